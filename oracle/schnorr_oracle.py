@@ -1,0 +1,409 @@
+"""CPU oracle for dusk-schnorr's sign / verify hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference`
+leg may import this module.  The product (`schnorr_b200/`) never does.
+
+PARITY STATUS: **parity unpinned against the real crate.**  The reference (`/root/reference`,
+dusk-schnorr 0.18.0) holds no known-answer vectors and its arithmetic lives in
+un-vendored crates that cannot be built here (no Rust toolchain, no network):
+    dusk-bls12_381 ^0.13, dusk-jubjub ^0.14, dusk-poseidon ^0.33 (-> dusk-hades ^0.24),
+    ff ^0.13, rand_core ^0.6, rand ^0.8 (StdRng = ChaCha12, rand_chacha 0.3)
+    [/root/reference/Cargo.toml:20-35].
+This file restates their *published algorithms* with exact Python integers and is anchored on
+the reference's own call sites (cited per function).  What pins it:
+  * self-validating constants: G and G' (GENERATOR / GENERATOR_NUMS of dusk-jubjub) are checked to
+    be on the curve and of prime order r -- a mis-recalled coordinate fails that with
+    overwhelming probability (tests/test_oracle.py);
+  * ChaCha: the 20-round variant of the same block function reproduces the RFC-7539-era
+    zero-key keystream, and the 12-round StdRng reproduces rand 0.8's own
+    `test_stdrng_construction` constants;
+  * the reference's behavioural tests (sign->verify true, wrong key false, bytes round-trip,
+    projective equality) re-run against this oracle (tests/test_reference_semantics.py).
+Nothing pins the Poseidon round constants / sponge padding numerically; the fingerprints in
+SURVEY.md §8(c) pin *this restatement* so drift is detected.
+
+Everything here is affine, big-int, slow and deliberately naive: scalar multiplication is the
+reference's 252-step MSB-first double-and-add, nothing is windowed, nothing is batched.
+"""
+from __future__ import annotations
+
+import hashlib
+import struct
+from typing import List, Optional, Sequence, Tuple
+
+# --------------------------------------------------------------------------------------------
+# Fields.  q = BLS12-381 scalar field (dusk_bls12_381::BlsScalar), r = JubJub scalar field
+# (dusk_jubjub::JubJubScalar).
+# --------------------------------------------------------------------------------------------
+Q = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+R = 0x0E7DB4EA6533AFA906673B0101343B00A6682093CCC81082D0970E5ED6F72CB7
+MONT_R = 1 << 256  # Montgomery radix used by the reference's 4x64 limbs and by the GPU's 8x32 limbs
+
+# JubJub: -u^2 + v^2 = 1 + d u^2 v^2,  d = -(10240/10241) mod q  (dusk-jubjub EDWARDS_D)
+D = (-10240 * pow(10241, -1, Q)) % Q
+
+Affine = Tuple[int, int]
+IDENTITY: Affine = (0, 1)
+
+# dusk_jubjub::GENERATOR (affine) -- used as GENERATOR_EXTENDED at
+# /root/reference/src/keys/secret.rs:159, /root/reference/src/keys/public.rs:63,127
+G: Affine = (0x3FD2814C43AC65A6F1FBF02D0FD6CCE62E3EBB21FD6C54ED4DF7B7FFEC7BEACA, 0x12)
+# dusk_jubjub::GENERATOR_NUMS (affine) -- GENERATOR_NUMS_EXTENDED at
+# /root/reference/src/keys/secret.rs:232, /root/reference/src/keys/public.rs:239,268
+G_NUMS: Affine = (
+    0x5E67B8F316F414F7BD9514C773FD4456931E316A39FE4541921710179DF76377,
+    0x43D80EB3B2F3EB1B7B162DBEEB3B34FD9949BA0F82A5507A6705B707162E3EF8,
+)
+
+
+def fq_inv(x: int) -> int:
+    return pow(x, -1, Q)
+
+
+def on_curve(p: Affine) -> bool:
+    u, v = p
+    return (-u * u + v * v - 1 - D * u * u % Q * v * v) % Q == 0
+
+
+def pt_add(p: Affine, s: Affine) -> Affine:
+    """Complete twisted-Edwards addition, a = -1 (what `JubJubExtended + JubJubExtended` computes
+    up to projective representation; /root/reference/src/keys/public.rs:127)."""
+    u1, v1 = p
+    u2, v2 = s
+    t = D * u1 % Q * u2 % Q * v1 % Q * v2 % Q
+    u3 = (u1 * v2 + v1 * u2) % Q * fq_inv((1 + t) % Q) % Q
+    v3 = (v1 * v2 + u1 * u2) % Q * fq_inv((1 - t) % Q) % Q
+    return (u3, v3)
+
+
+def pt_neg(p: Affine) -> Affine:
+    return ((-p[0]) % Q, p[1])
+
+
+def pt_mul(p: Affine, s: int) -> Affine:
+    """`JubJubExtended * JubJubScalar`: 252 iterations MSB-first over the canonical little-endian
+    bytes of s, skipping the top 4 bits: acc = 2*acc; acc += bit ? P : identity.
+    Call sites: /root/reference/src/keys/public.rs:63,127,236-239,340,411-412 and
+    /root/reference/src/keys/secret.rs:159,231-232,373,440."""
+    assert 0 <= s < (1 << 252)
+    acc = IDENTITY
+    for i in range(251, -1, -1):
+        acc = pt_add(acc, acc)
+        if (s >> i) & 1:
+            acc = pt_add(acc, p)
+    return acc
+
+
+# Faster exact path (projective, integer-only) used to generate large fixtures; validated
+# against pt_mul in tests/test_oracle.py.
+def _ext_add(p, s):
+    x1, y1, z1, t1 = p
+    x2, y2, z2, t2 = s
+    a = (y1 - x1) * (y2 - x2) % Q
+    b = (y1 + x1) * (y2 + x2) % Q
+    c = t1 * 2 * D % Q * t2 % Q
+    dd = 2 * z1 * z2 % Q
+    e, f, g, h = (b - a) % Q, (dd - c) % Q, (dd + c) % Q, (b + a) % Q
+    return (e * f % Q, g * h % Q, f * g % Q, e * h % Q)
+
+
+def pt_mul_fast(p: Affine, s: int) -> Affine:
+    acc = (0, 1, 1, 0)
+    base = (p[0], p[1], 1, p[0] * p[1] % Q)
+    for i in range(s.bit_length() - 1, -1, -1):
+        acc = _ext_add(acc, acc)
+        if (s >> i) & 1:
+            acc = _ext_add(acc, base)
+    zi = fq_inv(acc[2])
+    return (acc[0] * zi % Q, acc[1] * zi % Q)
+
+
+def proj_eq(p: Tuple[int, int, int], s: Tuple[int, int, int]) -> bool:
+    """`JubJubExtended == JubJubExtended`: u1*z2 == u2*z1 and v1*z2 == v2*z1
+    (pinned by /root/reference/tests/keys.rs:52-58)."""
+    return (p[0] * s[2] - s[0] * p[2]) % Q == 0 and (p[1] * s[2] - s[1] * p[2]) % Q == 0
+
+
+# --------------------------------------------------------------------------------------------
+# Serialization (dusk_bytes::Serializable on the jubjub types)
+# --------------------------------------------------------------------------------------------
+def fq_sqrt(a: int) -> Optional[int]:
+    """Tonelli-Shanks in F_q (2-adicity 32)."""
+    a %= Q
+    if a == 0:
+        return 0
+    if pow(a, (Q - 1) // 2, Q) != 1:
+        return None
+    s, t = 0, Q - 1
+    while t % 2 == 0:
+        s, t = s + 1, t // 2
+    z = 2
+    while pow(z, (Q - 1) // 2, Q) != Q - 1:
+        z += 1
+    m, c, tt, res = s, pow(z, t, Q), pow(a, t, Q), pow(a, (t + 1) // 2, Q)
+    while tt != 1:
+        i, x = 0, tt
+        while x != 1:
+            x, i = x * x % Q, i + 1
+        b = pow(c, 1 << (m - i - 1), Q)
+        m, c = i, b * b % Q
+        tt, res = tt * c % Q, res * b % Q
+    return res
+
+
+def affine_to_bytes(p: Affine) -> bytes:
+    """JubJubAffine::to_bytes: LE bytes of v, bit 255 := lowest bit of u.  Used by
+    Signature::to_bytes /root/reference/src/signatures.rs:109-114 and PublicKey::to_bytes
+    /root/reference/src/keys/public.rs:90-92."""
+    b = bytearray(p[1].to_bytes(32, "little"))
+    b[31] |= (p[0] & 1) << 7
+    return bytes(b)
+
+
+def affine_from_bytes(b: bytes) -> Optional[Affine]:
+    """JubJubAffine::from_bytes: no subgroup check (/root/reference/src/keys/public.rs:94-100)."""
+    assert len(b) == 32
+    sign = b[31] >> 7
+    v = int.from_bytes(b, "little") & ((1 << 255) - 1)
+    if v >= Q:
+        return None
+    v2 = v * v % Q
+    den = (1 + D * v2) % Q
+    if den == 0:
+        u2 = 0
+    else:
+        u2 = (v2 - 1) * fq_inv(den) % Q
+    u = fq_sqrt(u2)
+    if u is None:
+        return None
+    if (u & 1) != sign:
+        u = (-u) % Q
+    return (u, v)
+
+
+def scalar_from_bytes(b: bytes) -> Optional[int]:
+    """JubJubScalar::from_bytes rejects >= r (/root/reference/src/keys/secret.rs:96-102)."""
+    x = int.from_bytes(b, "little")
+    return x if x < R else None
+
+
+# --------------------------------------------------------------------------------------------
+# Hades252 permutation + Poseidon sponge (dusk-hades 0.24 / dusk-poseidon 0.33)
+# --------------------------------------------------------------------------------------------
+WIDTH = 5
+FULL_ROUNDS = 8
+PARTIAL_ROUNDS = 59
+N_CONSTANTS = 960
+
+
+def _round_constants() -> List[int]:
+    """dusk-hades `ark.bin`: b = "poseidon-for-plonk"; repeat b = SHA-512(b);
+    constant = BlsScalar::from_bytes_wide(b)."""
+    out, b = [], b"poseidon-for-plonk"
+    for _ in range(N_CONSTANTS):
+        b = hashlib.sha512(b).digest()
+        out.append(int.from_bytes(b, "little") % Q)
+    return out
+
+
+ROUND_CONSTANTS = _round_constants()
+# dusk-hades `mds.bin`: Cauchy matrix 1/(x_i + y_j), x_i = i, y_j = WIDTH + j.
+MDS = [[fq_inv(i + j + WIDTH) for j in range(WIDTH)] for i in range(WIDTH)]
+
+
+def hades_perm(state: Sequence[int]) -> List[int]:
+    """ScalarStrategy::perm: 4 full, 59 partial, 4 full rounds; each round = add 5 round keys,
+    S-box x^5 (partial: last word only), multiply by MDS (result[k] = sum_j MDS[k][j] * s[j])."""
+    s = list(state)
+    assert len(s) == WIDTH
+    ci = 0
+    for rnd in range(FULL_ROUNDS + PARTIAL_ROUNDS):
+        for k in range(WIDTH):
+            s[k] = (s[k] + ROUND_CONSTANTS[ci]) % Q
+            ci += 1
+        full = rnd < FULL_ROUNDS // 2 or rnd >= FULL_ROUNDS // 2 + PARTIAL_ROUNDS
+        if full:
+            s = [pow(x, 5, Q) for x in s]
+        else:
+            s[WIDTH - 1] = pow(s[WIDTH - 1], 5, Q)
+        s = [sum(MDS[k][j] * s[j] for j in range(WIDTH)) % Q for k in range(WIDTH)]
+    return s
+
+
+def sponge_hash(msgs: Sequence[int]) -> int:
+    """dusk_poseidon::sponge::hash: capacity word 0, rate 4, absorb by addition; a short last
+    chunk gets `1` added after its last element; a full last chunk is permuted, then `1` is
+    added to word 1; output word 1."""
+    state = [0] * WIDTH
+    l = len(msgs)
+    m = l // (WIDTH - 1)
+    n = m * (WIDTH - 1)
+    last_iteration = max(m - 1, 0) if l == n else l // (WIDTH - 1)
+    chunks = [msgs[i:i + WIDTH - 1] for i in range(0, l, WIDTH - 1)]
+    for i, chunk in enumerate(chunks):
+        for k, c in enumerate(chunk):
+            state[1 + k] = (state[1 + k] + c) % Q
+        if i == last_iteration and len(chunk) < WIDTH - 1:
+            state[len(chunk) + 1] = (state[len(chunk) + 1] + 1) % Q
+        elif i == last_iteration:
+            state = hades_perm(state)
+            state[1] = (state[1] + 1) % Q
+        state = hades_perm(state)
+    return state[1]
+
+
+def truncated_hash(msgs: Sequence[int]) -> int:
+    """dusk_poseidon::sponge::truncated::hash: low 250 bits of the sponge output, as a
+    JubJubScalar (2^250 < r).  Called at /root/reference/src/signatures.rs:133,283-289."""
+    return sponge_hash(msgs) & ((1 << 250) - 1)
+
+
+# --------------------------------------------------------------------------------------------
+# The scheme layer, function for function
+# --------------------------------------------------------------------------------------------
+def challenge_hash(R_aff: Affine, msg: int) -> int:
+    """/root/reference/src/signatures.rs:127-134 (R.to_hash_inputs() = affine (u, v))."""
+    return truncated_hash([R_aff[0], R_aff[1], msg])
+
+
+def challenge_hash_double(R_aff: Affine, Rp_aff: Affine, msg: int) -> int:
+    """/root/reference/src/signatures.rs:275-290."""
+    return truncated_hash([R_aff[0], R_aff[1], Rp_aff[0], Rp_aff[1], msg])
+
+
+def keygen(sk: int) -> Affine:
+    """PublicKey::from(&SecretKey): /root/reference/src/keys/public.rs:61-67."""
+    return pt_mul(G, sk)
+
+
+def keygen_double(sk: int) -> Tuple[Affine, Affine]:
+    """PublicKeyDouble::from(&SecretKey): /root/reference/src/keys/public.rs:265-272."""
+    return pt_mul(G, sk), pt_mul(G_NUMS, sk)
+
+
+def keygen_vargen(sk: int, gen: Affine) -> Affine:
+    """PublicKeyVarGen::from(&SecretKeyVarGen): /root/reference/src/keys/public.rs:337-344."""
+    return pt_mul(gen, sk)
+
+
+def sign(sk: int, nonce: int, msg: int, mul=pt_mul) -> Tuple[int, Affine, int]:
+    """SecretKey::sign, /root/reference/src/keys/secret.rs:150-168, with the nonce r (the single
+    JubJubScalar::random draw of line 155) passed in.  Returns (u, R affine, c)."""
+    Rp = mul(G, nonce)
+    c = challenge_hash(Rp, msg)
+    u = (nonce - c * sk) % R
+    return u, Rp, c
+
+
+def sign_double(sk: int, nonce: int, msg: int, mul=pt_mul) -> Tuple[int, Affine, Affine, int]:
+    """SecretKey::sign_double, /root/reference/src/keys/secret.rs:217-240."""
+    Rp, Rpp = mul(G, nonce), mul(G_NUMS, nonce)
+    c = challenge_hash_double(Rp, Rpp, msg)
+    u = (nonce - c * sk) % R
+    return u, Rp, Rpp, c
+
+
+def sign_vargen(sk: int, gen: Affine, nonce: int, msg: int, mul=pt_mul) -> Tuple[int, Affine, int]:
+    """SecretKeyVarGen::sign, /root/reference/src/keys/secret.rs:433-451."""
+    Rp = mul(gen, nonce)
+    c = challenge_hash(Rp, msg)
+    u = (nonce - c * sk) % R
+    return u, Rp, c
+
+
+def verify(pk: Affine, u: int, R_aff: Affine, msg: int, mul=pt_mul) -> bool:
+    """PublicKey::verify, /root/reference/src/keys/public.rs:121-130."""
+    c = challenge_hash(R_aff, msg)
+    return pt_add(mul(G, u), mul(pk, c)) == R_aff
+
+
+def verify_double(pk: Affine, pkp: Affine, u: int, R_aff: Affine, Rp_aff: Affine, msg: int, mul=pt_mul) -> bool:
+    """PublicKeyDouble::verify, /root/reference/src/keys/public.rs:222-244."""
+    c = challenge_hash_double(R_aff, Rp_aff, msg)
+    p1 = pt_add(mul(G, u), mul(pk, c))
+    p2 = pt_add(mul(G_NUMS, u), mul(pkp, c))
+    return p1 == R_aff and p2 == Rp_aff
+
+
+def verify_vargen(pk: Affine, gen: Affine, u: int, R_aff: Affine, msg: int, mul=pt_mul) -> bool:
+    """PublicKeyVarGen::verify, /root/reference/src/keys/public.rs:401-415."""
+    c = challenge_hash(R_aff, msg)
+    return pt_add(mul(gen, u), mul(pk, c)) == R_aff
+
+
+# --------------------------------------------------------------------------------------------
+# The seeded RNG stream the reference's tests consume: rand 0.8 StdRng = ChaCha12
+# (/root/reference/tests/schnorr.rs:16 `StdRng::seed_from_u64(2321)`).
+# --------------------------------------------------------------------------------------------
+def _rotl(x: int, n: int) -> int:
+    return ((x << n) | (x >> (32 - n))) & 0xFFFFFFFF
+
+
+def chacha_block(key_words: Sequence[int], counter: int, stream: int = 0, rounds: int = 12) -> bytes:
+    """One 64-byte ChaCha block, 64-bit block counter (words 12-13), 64-bit stream id (14-15)."""
+    st = [0x61707865, 0x3320646E, 0x79622D32, 0x6B206574] + list(key_words) + [
+        counter & 0xFFFFFFFF, (counter >> 32) & 0xFFFFFFFF, stream & 0xFFFFFFFF, (stream >> 32) & 0xFFFFFFFF]
+    x = list(st)
+
+    def qr(a, b, c, d):
+        x[a] = (x[a] + x[b]) & 0xFFFFFFFF; x[d] = _rotl(x[d] ^ x[a], 16)
+        x[c] = (x[c] + x[d]) & 0xFFFFFFFF; x[b] = _rotl(x[b] ^ x[c], 12)
+        x[a] = (x[a] + x[b]) & 0xFFFFFFFF; x[d] = _rotl(x[d] ^ x[a], 8)
+        x[c] = (x[c] + x[d]) & 0xFFFFFFFF; x[b] = _rotl(x[b] ^ x[c], 7)
+
+    for _ in range(rounds // 2):
+        qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
+        qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
+    return struct.pack("<16I", *[(x[i] + st[i]) & 0xFFFFFFFF for i in range(16)])
+
+
+def seed_from_u64(state: int) -> bytes:
+    """rand_core 0.6 SeedableRng::seed_from_u64: PCG32 expansion of the u64 into a 32-byte seed."""
+    MUL, INC, M64 = 6364136223846793005, 11634580027462260723, (1 << 64) - 1
+    out = b""
+    for _ in range(8):
+        state = (state * MUL + INC) & M64
+        xorshifted = (((state >> 18) ^ state) >> 27) & 0xFFFFFFFF
+        rot = state >> 59
+        x = ((xorshifted >> rot) | (xorshifted << ((32 - rot) & 31))) & 0xFFFFFFFF
+        out += struct.pack("<I", x)
+    return out
+
+
+class StdRng:
+    """rand 0.8 `StdRng` restricted to what the hot path draws: whole little-endian words,
+    consumed in order.  Every draw on the path is 64 B = one ChaCha block."""
+
+    def __init__(self, seed: bytes):
+        assert len(seed) == 32
+        self.key = struct.unpack("<8I", seed)
+        self.block = 0
+        self.buf = b""
+
+    @classmethod
+    def seed_from_u64(cls, s: int) -> "StdRng":
+        return cls(seed_from_u64(s))
+
+    def fill_bytes(self, n: int) -> bytes:
+        assert n % 4 == 0
+        while len(self.buf) < n:
+            self.buf += chacha_block(self.key, self.block)
+            self.block += 1
+        out, self.buf = self.buf[:n], self.buf[n:]
+        return out
+
+    def next_u64(self) -> int:
+        return int.from_bytes(self.fill_bytes(8), "little")
+
+    def random_fr(self) -> int:
+        """JubJubScalar::random = from_bytes_wide(64 RNG bytes) (/root/reference/src/keys/secret.rs:83,155)."""
+        return int.from_bytes(self.fill_bytes(64), "little") % R
+
+    def random_fq(self) -> int:
+        """BlsScalar::random (/root/reference/tests/schnorr.rs:19)."""
+        return int.from_bytes(self.fill_bytes(64), "little") % Q
+
+
+def nonce_from_block(key_words: Sequence[int], i: int) -> int:
+    """Nonce i of an rng used only for signing = from_bytes_wide(ChaCha12 block i)."""
+    return int.from_bytes(chacha_block(key_words, i), "little") % R

@@ -1,0 +1,123 @@
+// Integer-multiply roofline microbenchmark for B200 (sm_100a).
+// Measures sustained issue rates of the instructions the Fq/Fr Montgomery code is made of:
+//   mad.lo.u32 (IMAD), mad.hi.u32 (IMAD.HI), mad.wide.u32 (IMAD.WIDE), the carry-chained
+//   mad.lo.cc/madc.hi.cc pair (IMAD.WIDE.X), add.cc chains (IADD3), and a 1:1 wide+add mix.
+// Prints one JSON object: per-instruction results/clk/SM (from clock64 inside the kernel) and
+// results/s for the whole GPU (from CUDA events).  Used as the denominator of roofline.frac.
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { \
+  fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); return 1; } } while (0)
+
+constexpr int ITERS = 4096;
+constexpr int CHAINS = 8;
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k(uint32_t* out, long long* cycles, uint32_t seed) {
+  uint32_t a = seed + threadIdx.x, b = seed * 2654435761u + blockIdx.x;
+  uint32_t b1 = b ^ 0x55555555u, b2 = b + 77u, b3 = b * 3u;
+  uint32_t x[CHAINS];   // 32-bit chains
+  uint64_t v[CHAINS];   // 64-bit chains (aligned register pairs)
+  double d[CHAINS];
+#pragma unroll
+  for (int i = 0; i < CHAINS; i++) {
+    x[i] = a ^ (i * 0x9e3779b9u);
+    v[i] = ((uint64_t)(b + i) << 32) | x[i];
+    d[i] = 1.0 + 1e-3 * (double)(x[i] & 1023);
+  }
+  long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < ITERS; it++) {
+    if (MODE == 0) {  // IMAD (mad.lo), multiplicand = running value so ptxas cannot hoist the product
+#pragma unroll
+      for (int c = 0; c < CHAINS; c++) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(a), "r"(b));
+    } else if (MODE == 1) {  // IMAD.HI
+#pragma unroll
+      for (int c = 0; c < CHAINS; c++) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(a), "r"(b));
+    } else if (MODE == 2) {  // IMAD.WIDE.U32: 32x32 + 64 -> 64, no carry out
+#pragma unroll
+      for (int c = 0; c < CHAINS; c++)
+        asm volatile("{\n\t.reg .u32 l,h;\n\tmov.b64 {l,h}, %2;\n\tmad.wide.u32 %0, l, %1, %0;\n\t}" : "+l"(v[c]) : "r"(a), "l"(v[(c + 3) % CHAINS]));
+    } else if (MODE == 3) {
+      // two independent 4-product carry chains: (mad.lo.cc, madc.hi.cc) x4 -> IMAD.WIDE.U32 + 3x IMAD.WIDE.U32.X
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        asm volatile(
+            "{\n\t.reg .u32 l0,h0,l1,h1,l2,h2,l3,h3;\n\t"
+            "mov.b64 {l0,h0}, %0; mov.b64 {l1,h1}, %1; mov.b64 {l2,h2}, %2; mov.b64 {l3,h3}, %3;\n\t"
+            "mad.lo.cc.u32 l0, %4, %5, l0;\n\t"
+            "madc.hi.cc.u32 h0, %4, %5, h0;\n\t"
+            "madc.lo.cc.u32 l1, %4, %6, l1;\n\t"
+            "madc.hi.cc.u32 h1, %4, %6, h1;\n\t"
+            "madc.lo.cc.u32 l2, %4, %7, l2;\n\t"
+            "madc.hi.cc.u32 h2, %4, %7, h2;\n\t"
+            "madc.lo.cc.u32 l3, %4, %8, l3;\n\t"
+            "madc.hi.u32 h3, %4, %8, h3;\n\t"
+            "mov.b64 %0, {l0,h0}; mov.b64 %1, {l1,h1}; mov.b64 %2, {l2,h2}; mov.b64 %3, {l3,h3};\n\t}"
+            : "+l"(v[4 * h]), "+l"(v[4 * h + 1]), "+l"(v[4 * h + 2]), "+l"(v[4 * h + 3])
+            : "r"(a), "r"(b), "r"(b1), "r"(b2), "r"(b3));
+      }
+    } else if (MODE == 4) {  // 64-bit add as add.cc/addc pair (ALU-pipe IADD3 [+ IMAD.X])
+#pragma unroll
+      for (int c = 0; c < CHAINS; c++)
+        asm volatile("{\n\t.reg .u32 l,h;\n\tmov.b64 {l,h}, %0;\n\tadd.cc.u32 l, l, %1;\n\taddc.u32 h, h, %2;\n\tmov.b64 %0, {l,h};\n\t}"
+                     : "+l"(v[c]) : "r"(a), "r"(b));
+    } else if (MODE == 5) {  // mix: 4 wide products + 4 lop3/shf-type ALU ops on other registers
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        asm volatile("{\n\t.reg .u32 l,h;\n\tmov.b64 {l,h}, %2;\n\tmad.wide.u32 %0, l, %1, %0;\n\t}" : "+l"(v[c]) : "r"(a), "l"(v[(c + 1) % 4]));
+        asm volatile("add.u32 %0, %0, %1;" : "+r"(x[c]) : "r"(b));
+        asm volatile("xor.b32 %0, %0, %1;" : "+r"(x[4 + c]) : "r"(a));
+      }
+    } else if (MODE == 6) {  // DFMA
+#pragma unroll
+      for (int c = 0; c < CHAINS; c++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[c]) : "d"(1.0000001), "d"(1e-9));
+    }
+  }
+  long long t1 = clock64();
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < CHAINS; i++) acc ^= x[i] ^ (uint32_t)v[i] ^ (uint32_t)(v[i] >> 32) ^ (uint32_t)__double2loint(d[i]);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int MODE>
+int run(const char* name, double ops_per_iter, int nsm, int ctas_per_sm, uint32_t* out, long long* cyc, bool last) {
+  int grid = nsm * ctas_per_sm, block = 256;
+  for (int w = 0; w < 2; w++) k<MODE><<<grid, block>>>(out, cyc, 12345u + w);
+  CK(cudaDeviceSynchronize());
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0));
+  const int REP = 5;
+  for (int r = 0; r < REP; r++) k<MODE><<<grid, block>>>(out, cyc, 999u + r);
+  CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+  float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= REP;
+  long long* h = (long long*)malloc(sizeof(long long) * grid);
+  CK(cudaMemcpy(h, cyc, sizeof(long long) * grid, cudaMemcpyDeviceToHost));
+  double avg = 0; for (int i = 0; i < grid; i++) avg += (double)h[i]; avg /= grid; free(h);
+  double total_ops = ops_per_iter * ITERS * (double)block * grid;
+  double per_clk_sm = ops_per_iter * ITERS * (double)block * ctas_per_sm / avg;  // thread-level results / clk / SM
+  printf("  \"%s\": {\"per_clk_sm\": %.2f, \"per_s\": %.4e, \"ms\": %.4f, \"eff_mhz\": %.0f}%s\n", name, per_clk_sm,
+         total_ops / (ms * 1e-3), ms, avg / (ms * 1e3), last ? "" : ",");
+  return 0;
+}
+
+int main() {
+  cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+  int nsm = p.multiProcessorCount, cps = 8;  // 8 CTAs x 256 thr = 64 warps/SM (full occupancy)
+  uint32_t* out; long long* cyc;
+  CK(cudaMalloc(&out, sizeof(uint32_t) * nsm * cps * 256)); CK(cudaMalloc(&cyc, sizeof(long long) * nsm * cps));
+  printf("{\n  \"gpu\": \"%s\", \"sms\": %d, \"clock_khz_max\": %d,\n", p.name, nsm, p.clockRate);
+  if (run<0>("imad_lo", CHAINS, nsm, cps, out, cyc, false)) return 1;
+  if (run<1>("imad_hi", CHAINS, nsm, cps, out, cyc, false)) return 1;
+  if (run<2>("imad_wide", CHAINS, nsm, cps, out, cyc, false)) return 1;
+  if (run<3>("imad_wide_cc", 8, nsm, cps, out, cyc, false)) return 1;   // 8 wide products / iter
+  if (run<4>("iadd64_pair", CHAINS, nsm, cps, out, cyc, false)) return 1;  // 16 adds / iter
+  if (run<5>("mix_wide4_alu8", 4, nsm, cps, out, cyc, false)) return 1;  // counts the 4 wide products
+  if (run<6>("dfma", CHAINS, nsm, cps, out, cyc, true)) return 1;
+  printf("}\n");
+  return 0;
+}
