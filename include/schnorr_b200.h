@@ -1,0 +1,121 @@
+/* schnorr_b200 -- C ABI of the B200 batch engine for dusk-schnorr's sign / verify hot path.
+ *
+ * The reference (dusk-schnorr 0.18.0, pure Rust) has no FFI; its boundary for this path is the
+ * crate's public API.  Each entry point below is the batch form of one reference method and is what
+ * a `#[link(name = "schnorr_b200")] extern "C"` block in the crate would bind:
+ *
+ *   sb200_verify          PublicKey::verify            /root/reference/src/keys/public.rs:121-130
+ *   sb200_verify_double   PublicKeyDouble::verify      /root/reference/src/keys/public.rs:222-244
+ *   sb200_verify_vargen   PublicKeyVarGen::verify      /root/reference/src/keys/public.rs:401-415
+ *   sb200_sign            SecretKey::sign              /root/reference/src/keys/secret.rs:150-168
+ *   sb200_sign_double     SecretKey::sign_double       /root/reference/src/keys/secret.rs:217-240
+ *   sb200_sign_vargen     SecretKeyVarGen::sign        /root/reference/src/keys/secret.rs:433-451
+ *   sb200_keygen          PublicKey::from(&SecretKey)          /root/reference/src/keys/public.rs:61-67
+ *   sb200_keygen_double   PublicKeyDouble::from(&SecretKey)    /root/reference/src/keys/public.rs:265-272
+ *   sb200_keygen_vargen   PublicKeyVarGen::from(&SecretKeyVarGen) /root/reference/src/keys/public.rs:337-344
+ *
+ * Data layout (all arrays are caller-owned, tuple-major, tightly packed, 16-byte aligned):
+ *   field element (BlsScalar: message, point coordinates) = 8 x u32 little-endian limbs in
+ *       MONTGOMERY form (x * 2^256 mod q) -- bit-identical to `BlsScalar.0: [u64; 4]` on a
+ *       little-endian host, so Rust hands over its internal limbs without conversion.  Must be < q.
+ *   scalar (JubJubScalar: sk, nonce, u, c) = 8 x u32 little-endian limbs of the CANONICAL integer
+ *       (= `JubJubScalar::to_bytes()`), must be < r.  A `u` >= r makes that tuple's verdict 0.
+ *   point  = SB200_POINTS_AFFINE:      (u, v)      2 field elements (64 B);
+ *            SB200_POINTS_PROJECTIVE:  (U, V, Z)   3 field elements (96 B), Z != 0 -- the
+ *            (u, v, z) of a JubJubExtended; t1/t2 are not needed.  Points must be on the curve
+ *            (the reference can only produce on-curve points outside `from_raw_unchecked`).
+ *       One flag applies to every point array of the call.  Points written by the library are
+ *       always affine (u, v), Montgomery form.
+ *   verdicts = bitmap, bit (i & 31) of word (i >> 5) is tuple i's `verify` result; ceil(n/32) words.
+ *
+ * Nonces are an INPUT (`nonce[i]` is the one `JubJubScalar::random(rng)` draw of signature i,
+ * /root/reference/src/keys/secret.rs:155): the RNG stays on the host; the library never generates
+ * randomness.
+ *
+ * Threading: one batch in flight per context (calls on one context are serialised by an internal
+ * mutex); distinct contexts are independent.  Calls block until the outputs are in host memory,
+ * except with SB200_DEVICE_PTRS (see below).  No call aborts; errors are return codes.
+ * There is no CPU fallback: without a usable CUDA device sb200_init fails with SB200_ERR_NODEV.
+ */
+#ifndef SCHNORR_B200_H
+#define SCHNORR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sb200_ctx sb200_ctx;
+
+enum {
+  SB200_OK = 0,
+  SB200_ERR_ARG = -1,   /* null pointer, n < 0, unknown flag, misaligned buffer */
+  SB200_ERR_CUDA = -2,  /* a CUDA call failed; sb200_last_error() has the text */
+  SB200_ERR_NODEV = -3, /* no usable sm_100 device */
+  SB200_ERR_NOMEM = -4
+};
+
+#define SB200_POINTS_PROJECTIVE 0u
+#define SB200_POINTS_AFFINE 1u
+/* All buffers are device pointers on the context's (single) device; the call enqueues its kernel on
+ * the stream set with sb200_set_stream and returns without synchronising. */
+#define SB200_DEVICE_PTRS 2u
+
+/* devices: CUDA ordinals to shard over (tuples are split into contiguous blocks, multiples of 32);
+ * n_devices = 0 means "device 0".  Builds the comb tables of G and G' on every device. */
+int sb200_init(const int* devices, int n_devices, sb200_ctx** out);
+void sb200_destroy(sb200_ctx* ctx);
+const char* sb200_strerror(int code);
+const char* sb200_last_error(const sb200_ctx* ctx);
+int sb200_device_count(const sb200_ctx* ctx);
+/* stream (a cudaStream_t) used by SB200_DEVICE_PTRS calls; NULL = the legacy default stream */
+int sb200_set_stream(sb200_ctx* ctx, void* cuda_stream);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+uint64_t sb200_launch_count(const sb200_ctx* ctx);
+/* pinned host memory for full-speed host<->device copies (pageable memory also works, slower) */
+int sb200_host_alloc(size_t bytes, void** out);
+void sb200_host_free(void* p);
+
+/* c_out (n x 8 u32, canonical challenge scalars) may be NULL in every call below. */
+int sb200_verify(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* pk, const uint32_t* sig_u,
+                 const uint32_t* sig_R, const uint32_t* msg, uint32_t* verdicts, uint32_t* c_out);
+int sb200_verify_double(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* pk, const uint32_t* pk_prime,
+                        const uint32_t* sig_u, const uint32_t* sig_R, const uint32_t* sig_R_prime, const uint32_t* msg,
+                        uint32_t* verdicts, uint32_t* c_out);
+int sb200_verify_vargen(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* pk, const uint32_t* generator,
+                        const uint32_t* sig_u, const uint32_t* sig_R, const uint32_t* msg, uint32_t* verdicts,
+                        uint32_t* c_out);
+
+/* u_out: n x 8 u32 canonical; R_out (and R_prime_out): n x 16 u32 affine (u, v) Montgomery. */
+int sb200_sign(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* sk, const uint32_t* msg, const uint32_t* nonce,
+               uint32_t* u_out, uint32_t* R_out, uint32_t* c_out);
+int sb200_sign_double(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* sk, const uint32_t* msg,
+                      const uint32_t* nonce, uint32_t* u_out, uint32_t* R_out, uint32_t* R_prime_out, uint32_t* c_out);
+int sb200_sign_vargen(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* sk, const uint32_t* generator,
+                      const uint32_t* msg, const uint32_t* nonce, uint32_t* u_out, uint32_t* R_out, uint32_t* c_out);
+
+/* pk_out: n x 16 u32 affine (u, v) Montgomery */
+int sb200_keygen(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* sk, uint32_t* pk_out);
+int sb200_keygen_double(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* sk, uint32_t* pk_out,
+                        uint32_t* pk_prime_out);
+int sb200_keygen_vargen(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* sk, const uint32_t* generator,
+                        uint32_t* pk_out);
+
+/* Building-block probes for the parity tests (same kernels' device functions, one element per thread).
+ * op: 0 mul (Montgomery product), 1 add, 2 sub, 3 inverse (b ignored), 4 square, 5 to_mont, 6 from_mont */
+int sb200_dbg_fq(sb200_ctx* ctx, int64_t n, int op, const uint32_t* a, const uint32_t* b, uint32_t* out);
+/* canonical product a*b mod r */
+int sb200_dbg_fr_mul(sb200_ctx* ctx, int64_t n, const uint32_t* a, const uint32_t* b, uint32_t* out);
+/* Hades252 permutation of n states (5 field elements each, in place); dense != 0 runs the
+ * reference-shaped dense partial rounds instead of the sparse factorisation. */
+int sb200_dbg_hades(sb200_ctx* ctx, int64_t n, int dense, uint32_t* states);
+/* out[i] = k[i] * P[i] (affine); base: 0 = fixed G, 1 = fixed G', 2 = variable (points given) */
+int sb200_dbg_scalar_mul(sb200_ctx* ctx, int64_t n, uint32_t flags, int base, const uint32_t* points,
+                         const uint32_t* k, uint32_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCHNORR_B200_H */

@@ -1,0 +1,8 @@
+"""schnorr_b200: B200-native batch engine for dusk-schnorr's sign / verify hot path.
+
+Layout: `csrc/` holds the CUDA kernels and the C ABI (`include/schnorr_b200.h`);
+`_lib.py` binds the ABI with ctypes; `api.py` mirrors the reference crate's types
+(SecretKey, PublicKey, Signature, the Double and VarGen variants) on top of it.
+There is no CPU fallback anywhere in this package.
+"""
+from ._lib import DEVICE_PTRS, POINTS_AFFINE, POINTS_PROJECTIVE, Engine, SchnorrB200Error, load_library  # noqa: F401

@@ -1,0 +1,259 @@
+"""ctypes binding of libschnorr_b200.so (the C ABI in include/schnorr_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing or no B200 is visible, construction of an
+`Engine` raises.  numpy arrays are the host buffers (uint32, C-contiguous, 16-byte aligned).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libschnorr_b200.so")
+
+POINTS_PROJECTIVE = 0
+POINTS_AFFINE = 1
+DEVICE_PTRS = 2
+
+_lib = None
+
+
+class SchnorrB200Error(RuntimeError):
+    pass
+
+
+def load_library() -> ctypes.CDLL:
+    """Load the shared library (no CUDA call is made until an Engine is created)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SchnorrB200Error(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, u32p, i64, u32, ci = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32, ctypes.c_int
+    sig = {
+        "sb200_init": (ci, [ctypes.POINTER(ci), ci, ctypes.POINTER(vp)]),
+        "sb200_destroy": (None, [vp]),
+        "sb200_strerror": (ctypes.c_char_p, [ci]),
+        "sb200_last_error": (ctypes.c_char_p, [vp]),
+        "sb200_device_count": (ci, [vp]),
+        "sb200_set_stream": (ci, [vp, vp]),
+        "sb200_launch_count": (ctypes.c_uint64, [vp]),
+        "sb200_host_alloc": (ci, [ctypes.c_size_t, ctypes.POINTER(vp)]),
+        "sb200_host_free": (None, [vp]),
+        "sb200_verify": (ci, [vp, i64, u32] + [u32p] * 6),
+        "sb200_verify_double": (ci, [vp, i64, u32] + [u32p] * 8),
+        "sb200_verify_vargen": (ci, [vp, i64, u32] + [u32p] * 7),
+        "sb200_sign": (ci, [vp, i64, u32] + [u32p] * 6),
+        "sb200_sign_double": (ci, [vp, i64, u32] + [u32p] * 7),
+        "sb200_sign_vargen": (ci, [vp, i64, u32] + [u32p] * 7),
+        "sb200_keygen": (ci, [vp, i64, u32] + [u32p] * 2),
+        "sb200_keygen_double": (ci, [vp, i64, u32] + [u32p] * 3),
+        "sb200_keygen_vargen": (ci, [vp, i64, u32] + [u32p] * 3),
+        "sb200_dbg_fq": (ci, [vp, i64, ci] + [u32p] * 3),
+        "sb200_dbg_fr_mul": (ci, [vp, i64] + [u32p] * 3),
+        "sb200_dbg_hades": (ci, [vp, i64, ci, u32p]),
+        "sb200_dbg_scalar_mul": (ci, [vp, i64, u32, ci] + [u32p] * 3),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "sb200_init", "sb200_destroy", "sb200_strerror", "sb200_last_error", "sb200_device_count", "sb200_set_stream",
+    "sb200_launch_count", "sb200_host_alloc", "sb200_host_free", "sb200_verify", "sb200_verify_double",
+    "sb200_verify_vargen", "sb200_sign", "sb200_sign_double", "sb200_sign_vargen", "sb200_keygen",
+    "sb200_keygen_double", "sb200_keygen_vargen", "sb200_dbg_fq", "sb200_dbg_fr_mul", "sb200_dbg_hades",
+    "sb200_dbg_scalar_mul",
+]
+
+
+def aligned_empty(shape, dtype=np.uint32, align=64) -> np.ndarray:
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    raw = np.empty(n + align, dtype=np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + n].view(dtype).reshape(shape)
+
+
+def _arr(a, words: Optional[int], n: int, name: str) -> np.ndarray:
+    a = np.asarray(a)
+    if a.dtype != np.uint32:
+        raise SchnorrB200Error(f"{name}: expected uint32 limbs, got {a.dtype}")
+    if words is not None and a.size != n * words:
+        raise SchnorrB200Error(f"{name}: expected {n} x {words} u32, got {a.size}")
+    if not a.flags["C_CONTIGUOUS"] or a.ctypes.data % 16:
+        b = aligned_empty(a.shape)
+        b[...] = a
+        a = b
+    return a
+
+
+class Engine:
+    """One sb200 context: comb tables for G and G' resident on each device, two streams per device."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None):
+        self._lib = load_library()
+        devs = list(devices) if devices is not None else [0]
+        arr = (ctypes.c_int * len(devs))(*devs)
+        h = ctypes.c_void_p()
+        rc = self._lib.sb200_init(arr, len(devs), ctypes.byref(h))
+        if rc != 0:
+            raise SchnorrB200Error(f"sb200_init failed: {self._lib.sb200_strerror(rc).decode()} (no CPU fallback)")
+        self._h = h
+        self.devices = devs
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise SchnorrB200Error(
+                f"{what}: {self._lib.sb200_strerror(rc).decode()} {self._lib.sb200_last_error(self._h).decode()}")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.sb200_launch_count(self._h))
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self._lib.sb200_set_stream(self._h, ctypes.c_void_p(cuda_stream)), "set_stream")
+
+    # ---- raw pointer calls (device pointers with DEVICE_PTRS, used by bench.py) -------------
+    def call(self, name: str, n: int, flags: int, *ptrs: Optional[int]):
+        fn = getattr(self._lib, "sb200_" + name)
+        self._check(fn(self._h, n, flags, *[ctypes.c_void_p(p) if p else None for p in ptrs]), name)
+
+    # ---- numpy front-ends -----------------------------------------------------------------------
+    @staticmethod
+    def _pw(affine: bool) -> int:
+        return 16 if affine else 24
+
+    @staticmethod
+    def _unpack_bits(bitmap: np.ndarray, n: int) -> np.ndarray:
+        return np.unpackbits(bitmap.view(np.uint8), bitorder="little")[:n].astype(bool)
+
+    def verify(self, pk, u, R, msg, affine=True, want_c=True):
+        n = np.asarray(u).size // 8
+        pw, fl = self._pw(affine), POINTS_AFFINE if affine else POINTS_PROJECTIVE
+        pk, u, R, msg = _arr(pk, pw, n, "pk"), _arr(u, 8, n, "u"), _arr(R, pw, n, "R"), _arr(msg, 8, n, "msg")
+        bm = aligned_empty(((n + 31) // 32,)); bm[...] = 0
+        c = aligned_empty((n, 8)) if want_c else None
+        self.call("verify", n, fl, pk.ctypes.data, u.ctypes.data, R.ctypes.data, msg.ctypes.data, bm.ctypes.data,
+                  c.ctypes.data if want_c else None)
+        return self._unpack_bits(bm, n), c
+
+    def verify_double(self, pk, pkp, u, R, Rp, msg, affine=True, want_c=True):
+        n = np.asarray(u).size // 8
+        pw, fl = self._pw(affine), POINTS_AFFINE if affine else POINTS_PROJECTIVE
+        pk, pkp, R, Rp = _arr(pk, pw, n, "pk"), _arr(pkp, pw, n, "pk'"), _arr(R, pw, n, "R"), _arr(Rp, pw, n, "R'")
+        u, msg = _arr(u, 8, n, "u"), _arr(msg, 8, n, "msg")
+        bm = aligned_empty(((n + 31) // 32,)); bm[...] = 0
+        c = aligned_empty((n, 8)) if want_c else None
+        self.call("verify_double", n, fl, pk.ctypes.data, pkp.ctypes.data, u.ctypes.data, R.ctypes.data, Rp.ctypes.data,
+                  msg.ctypes.data, bm.ctypes.data, c.ctypes.data if want_c else None)
+        return self._unpack_bits(bm, n), c
+
+    def verify_vargen(self, pk, gen, u, R, msg, affine=True, want_c=True):
+        n = np.asarray(u).size // 8
+        pw, fl = self._pw(affine), POINTS_AFFINE if affine else POINTS_PROJECTIVE
+        pk, gen, R = _arr(pk, pw, n, "pk"), _arr(gen, pw, n, "gen"), _arr(R, pw, n, "R")
+        u, msg = _arr(u, 8, n, "u"), _arr(msg, 8, n, "msg")
+        bm = aligned_empty(((n + 31) // 32,)); bm[...] = 0
+        c = aligned_empty((n, 8)) if want_c else None
+        self.call("verify_vargen", n, fl, pk.ctypes.data, gen.ctypes.data, u.ctypes.data, R.ctypes.data, msg.ctypes.data,
+                  bm.ctypes.data, c.ctypes.data if want_c else None)
+        return self._unpack_bits(bm, n), c
+
+    def sign(self, sk, msg, nonce):
+        n = np.asarray(sk).size // 8
+        sk, msg, nonce = _arr(sk, 8, n, "sk"), _arr(msg, 8, n, "msg"), _arr(nonce, 8, n, "nonce")
+        u, R, c = aligned_empty((n, 8)), aligned_empty((n, 16)), aligned_empty((n, 8))
+        self.call("sign", n, 0, sk.ctypes.data, msg.ctypes.data, nonce.ctypes.data, u.ctypes.data, R.ctypes.data, c.ctypes.data)
+        return u, R, c
+
+    def sign_double(self, sk, msg, nonce):
+        n = np.asarray(sk).size // 8
+        sk, msg, nonce = _arr(sk, 8, n, "sk"), _arr(msg, 8, n, "msg"), _arr(nonce, 8, n, "nonce")
+        u, R, Rp, c = aligned_empty((n, 8)), aligned_empty((n, 16)), aligned_empty((n, 16)), aligned_empty((n, 8))
+        self.call("sign_double", n, 0, sk.ctypes.data, msg.ctypes.data, nonce.ctypes.data, u.ctypes.data, R.ctypes.data,
+                  Rp.ctypes.data, c.ctypes.data)
+        return u, R, Rp, c
+
+    def sign_vargen(self, sk, gen, msg, nonce, affine=True):
+        n = np.asarray(sk).size // 8
+        pw, fl = self._pw(affine), POINTS_AFFINE if affine else POINTS_PROJECTIVE
+        sk, msg, nonce, gen = _arr(sk, 8, n, "sk"), _arr(msg, 8, n, "msg"), _arr(nonce, 8, n, "nonce"), _arr(gen, pw, n, "gen")
+        u, R, c = aligned_empty((n, 8)), aligned_empty((n, 16)), aligned_empty((n, 8))
+        self.call("sign_vargen", n, fl, sk.ctypes.data, gen.ctypes.data, msg.ctypes.data, nonce.ctypes.data, u.ctypes.data,
+                  R.ctypes.data, c.ctypes.data)
+        return u, R, c
+
+    def keygen(self, sk):
+        n = np.asarray(sk).size // 8
+        sk = _arr(sk, 8, n, "sk")
+        pk = aligned_empty((n, 16))
+        self.call("keygen", n, 0, sk.ctypes.data, pk.ctypes.data)
+        return pk
+
+    def keygen_double(self, sk):
+        n = np.asarray(sk).size // 8
+        sk = _arr(sk, 8, n, "sk")
+        pk, pkp = aligned_empty((n, 16)), aligned_empty((n, 16))
+        self.call("keygen_double", n, 0, sk.ctypes.data, pk.ctypes.data, pkp.ctypes.data)
+        return pk, pkp
+
+    def keygen_vargen(self, sk, gen, affine=True):
+        n = np.asarray(sk).size // 8
+        pw, fl = self._pw(affine), POINTS_AFFINE if affine else POINTS_PROJECTIVE
+        sk, gen = _arr(sk, 8, n, "sk"), _arr(gen, pw, n, "gen")
+        pk = aligned_empty((n, 16))
+        self.call("keygen_vargen", n, fl, sk.ctypes.data, gen.ctypes.data, pk.ctypes.data)
+        return pk
+
+    # ---- building-block probes --------------------------------------------------------------------
+    def dbg_fq(self, op: int, a, b=None):
+        n = np.asarray(a).size // 8
+        a = _arr(a, 8, n, "a")
+        b = _arr(b, 8, n, "b") if b is not None else None
+        out = aligned_empty((n, 8))
+        rc = self._lib.sb200_dbg_fq(self._h, n, op, a.ctypes.data, b.ctypes.data if b is not None else None, out.ctypes.data)
+        self._check(rc, "dbg_fq")
+        return out
+
+    def dbg_fr_mul(self, a, b):
+        n = np.asarray(a).size // 8
+        a, b = _arr(a, 8, n, "a"), _arr(b, 8, n, "b")
+        out = aligned_empty((n, 8))
+        self._check(self._lib.sb200_dbg_fr_mul(self._h, n, a.ctypes.data, b.ctypes.data, out.ctypes.data), "dbg_fr_mul")
+        return out
+
+    def dbg_hades(self, states, dense=False):
+        n = np.asarray(states).size // 40
+        s = aligned_empty((n, 40)); s[...] = np.asarray(states, dtype=np.uint32).reshape(n, 40)
+        self._check(self._lib.sb200_dbg_hades(self._h, n, int(dense), s.ctypes.data), "dbg_hades")
+        return s
+
+    def dbg_scalar_mul(self, base: int, k, points=None, affine=True):
+        n = np.asarray(k).size // 8
+        pw, fl = self._pw(affine), POINTS_AFFINE if affine else POINTS_PROJECTIVE
+        k = _arr(k, 8, n, "k")
+        p = _arr(points, pw, n, "points") if points is not None else None
+        out = aligned_empty((n, 16))
+        rc = self._lib.sb200_dbg_scalar_mul(self._h, n, fl, base, p.ctypes.data if p is not None else None, k.ctypes.data, out.ctypes.data)
+        self._check(rc, "dbg_scalar_mul")
+        return out

@@ -1,0 +1,191 @@
+// Per-tuple sign / verify / keygen bodies (one tuple per thread).  Host+device so the exact code
+// the kernels run is also exercised on the CPU by tests/host_arith (test scaffolding only).
+//
+//   verify_core         PublicKey::verify        /root/reference/src/keys/public.rs:121-130
+//   verify_double_core  PublicKeyDouble::verify  /root/reference/src/keys/public.rs:222-244
+//   verify_vargen_core  PublicKeyVarGen::verify  /root/reference/src/keys/public.rs:401-415
+//   sign_core           SecretKey::sign          /root/reference/src/keys/secret.rs:150-168
+//   sign_double_core    SecretKey::sign_double   /root/reference/src/keys/secret.rs:217-240
+//   sign_vargen_core    SecretKeyVarGen::sign    /root/reference/src/keys/secret.rs:433-451
+//   keygen*_core        PublicKey*::from         /root/reference/src/keys/public.rs:61-67,265-272,337-344
+#pragma once
+#include "ed.cuh"
+#include "hades.cuh"
+
+namespace sb200 {
+
+struct point_in {  // a point as handed over the ABI: affine (Z absent => 1) or projective (U : V : Z)
+  fq U, V, Z;
+  bool affine;
+};
+
+SB_HD ext point_to_ext(const point_in& p) { return p.affine ? affine_to_ext(p.U, p.V) : proj_to_ext(p.U, p.V, p.Z); }
+
+// affine coordinates for hashing = `to_hash_inputs()` (JubJubAffine::from(extended): one inversion)
+SB_HD void point_to_affine(const point_in& p, fq& u, fq& v) {
+  if (p.affine) {
+    u = p.U;
+    v = p.V;
+  } else {
+    fq zi = fq_inv(p.Z);
+    u = fq_mul(p.U, zi);
+    v = fq_mul(p.V, zi);
+  }
+}
+
+// completed point == R (projective equality u1*z2 == u2*z1 && v1*z2 == v2*z1, /root/reference/tests/keys.rs:52-58);
+// with (X : Y : Z) = (E*F : G*H : F*G) this is E*Rz == Ru*G && H*Rz == Rv*F.
+SB_HD bool p1p1_equals(const p1p1& c, const point_in& R) {
+  fq l1 = R.affine ? c.E : fq_mul(c.E, R.Z);
+  fq l2 = R.affine ? c.H : fq_mul(c.H, R.Z);
+  return fq_eq(l1, fq_mul(R.U, c.G)) & fq_eq(l2, fq_mul(R.V, c.F));
+}
+
+SB_HD bool scalar_lt_r(const uint32_t* k) {
+  uint32_t t[8];
+  const uint32_t rr[8] = SB200_FR_MOD_INIT;
+  return sub8(t, k, rr) != 0;  // borrow <=> k < r
+}
+
+SB_HD bool verify_core(const point_in& PK, const uint32_t* u_in, const point_in& R, const fq& m, const uint32_t* combG,
+                       uint32_t* c_out) {
+  fq ru, rv;
+  point_to_affine(R, ru, rv);
+  uint32_t c[8];
+  challenge3(ru, rv, m, c);
+#pragma unroll
+  for (int i = 0; i < 8; i++) c_out[i] = c[i];
+  bool ok = scalar_lt_r(u_in);
+  uint32_t u[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) u[i] = ok ? u_in[i] : 0u;
+  pniels tab[9];
+  vartable_build(tab, point_to_ext(PK));
+  recode_offset<4>(c);
+  p1p1 cp = ed_mul_var(tab, c, 63);  // c < 2^250: 63 windows
+  recode_offset<8>(u);
+  cp = ed_comb_add(p1p1_to_ext(cp), combG, u);
+  return ok & p1p1_equals(cp, R);
+}
+
+SB_HD bool verify_vargen_core(const point_in& PK, const point_in& GEN, const uint32_t* u_in, const point_in& R,
+                              const fq& m, uint32_t* c_out) {
+  fq ru, rv;
+  point_to_affine(R, ru, rv);
+  uint32_t c[8];
+  challenge3(ru, rv, m, c);
+#pragma unroll
+  for (int i = 0; i < 8; i++) c_out[i] = c[i];
+  bool ok = scalar_lt_r(u_in);
+  uint32_t u[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) u[i] = ok ? u_in[i] : 0u;
+  pniels tabG[9], tabP[9];
+  vartable_build(tabG, point_to_ext(GEN));
+  vartable_build(tabP, point_to_ext(PK));
+  recode_offset<4>(c);
+  recode_offset<4>(u);
+  p1p1 cp = ed_mul_var2(tabG, u, tabP, c, 64);
+  return ok & p1p1_equals(cp, R);
+}
+
+SB_HD bool verify_double_core(const point_in& PK, const point_in& PKp, const uint32_t* u_in, const point_in& R,
+                              const point_in& Rp, const fq& m, const uint32_t* combG, const uint32_t* combGp,
+                              uint32_t* c_out) {
+  fq ru, rv, rpu, rpv;
+  if (R.affine) {
+    ru = R.U; rv = R.V; rpu = Rp.U; rpv = Rp.V;
+  } else {  // one shared inversion for Z and Z'
+    fq zz = fq_mul(R.Z, Rp.Z);
+    fq zi = fq_inv(zz);
+    fq zi1 = fq_mul(zi, Rp.Z), zi2 = fq_mul(zi, R.Z);
+    ru = fq_mul(R.U, zi1); rv = fq_mul(R.V, zi1);
+    rpu = fq_mul(Rp.U, zi2); rpv = fq_mul(Rp.V, zi2);
+  }
+  uint32_t c[8];
+  challenge5(ru, rv, rpu, rpv, m, c);
+#pragma unroll
+  for (int i = 0; i < 8; i++) c_out[i] = c[i];
+  bool ok = scalar_lt_r(u_in);
+  uint32_t u[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) u[i] = ok ? u_in[i] : 0u;
+  recode_offset<4>(c);
+  recode_offset<8>(u);
+  pniels tab[9];
+  vartable_build(tab, point_to_ext(PK));
+  p1p1 cp = ed_mul_var(tab, c, 63);
+  cp = ed_comb_add(p1p1_to_ext(cp), combG, u);
+  ok &= p1p1_equals(cp, R);
+  vartable_build(tab, point_to_ext(PKp));
+  cp = ed_mul_var(tab, c, 63);
+  cp = ed_comb_add(p1p1_to_ext(cp), combGp, u);
+  ok &= p1p1_equals(cp, Rp);
+  return ok;
+}
+
+SB_HD void ext_to_affine(const ext& p, fq& u, fq& v) {
+  fq zi = fq_inv(p.Z);
+  u = fq_mul(p.X, zi);
+  v = fq_mul(p.Y, zi);
+}
+
+// u = nonce - c * sk  (mod r)
+SB_HD void sign_finish(const uint32_t* nonce, const uint32_t* c, const uint32_t* sk, uint32_t* u_out) {
+  fr a, b, n;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    a.v[i] = c[i];
+    b.v[i] = sk[i];
+    n.v[i] = nonce[i];
+  }
+  fr u = fr_sub(n, fr_mul(a, b));
+#pragma unroll
+  for (int i = 0; i < 8; i++) u_out[i] = u.v[i];
+}
+
+// k*B for the fixed generator whose comb table is `comb`; k canonical (< 2^252)
+SB_HD ext fixed_base_mul(const uint32_t* comb, const uint32_t* k) {
+  uint32_t kr[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) kr[i] = k[i];
+  recode_offset<8>(kr);
+  return p1p1_to_ext(ed_comb_add(ext_identity(), comb, kr));
+}
+
+SB_HD ext var_base_mul(const point_in& P, const uint32_t* k) {
+  uint32_t kr[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) kr[i] = k[i];
+  recode_offset<4>(kr);
+  pniels tab[9];
+  vartable_build(tab, point_to_ext(P));
+  return p1p1_to_ext(ed_mul_var(tab, kr, 64));
+}
+
+SB_HD void sign_core(const uint32_t* sk, const uint32_t* nonce, const fq& m, const uint32_t* combG, uint32_t* u_out,
+                     fq& Ru, fq& Rv, uint32_t* c_out) {
+  ext_to_affine(fixed_base_mul(combG, nonce), Ru, Rv);
+  challenge3(Ru, Rv, m, c_out);
+  sign_finish(nonce, c_out, sk, u_out);
+}
+
+SB_HD void sign_double_core(const uint32_t* sk, const uint32_t* nonce, const fq& m, const uint32_t* combG,
+                            const uint32_t* combGp, uint32_t* u_out, fq& Ru, fq& Rv, fq& Rpu, fq& Rpv, uint32_t* c_out) {
+  ext a = fixed_base_mul(combG, nonce), b = fixed_base_mul(combGp, nonce);
+  fq zi = fq_inv(fq_mul(a.Z, b.Z));  // one inversion for both
+  fq zi1 = fq_mul(zi, b.Z), zi2 = fq_mul(zi, a.Z);
+  Ru = fq_mul(a.X, zi1); Rv = fq_mul(a.Y, zi1);
+  Rpu = fq_mul(b.X, zi2); Rpv = fq_mul(b.Y, zi2);
+  challenge5(Ru, Rv, Rpu, Rpv, m, c_out);
+  sign_finish(nonce, c_out, sk, u_out);
+}
+
+SB_HD void sign_vargen_core(const uint32_t* sk, const point_in& GEN, const uint32_t* nonce, const fq& m, uint32_t* u_out,
+                            fq& Ru, fq& Rv, uint32_t* c_out) {
+  ext_to_affine(var_base_mul(GEN, nonce), Ru, Rv);
+  challenge3(Ru, Rv, m, c_out);
+  sign_finish(nonce, c_out, sk, u_out);
+}
+
+}  // namespace sb200

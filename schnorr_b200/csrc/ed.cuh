@@ -1,0 +1,312 @@
+// JubJub group law for sm_100a: a = -1 twisted Edwards  -u^2 + v^2 = 1 + d u^2 v^2  over Fq.
+//
+// Replaces `JubJubExtended: Mul<JubJubScalar>, Add, PartialEq` (dusk-jubjub ^0.14) as used at
+// /root/reference/src/keys/public.rs:63,127-129,236-243,340,411-414 and
+// /root/reference/src/keys/secret.rs:159,231-232,373,440.
+//
+// -1 is a square and d a non-square in Fq, so the unified extended addition below is complete: no
+// exceptional cases for any pair of curve points (identity, small-order points, P + P, P - P).
+// The reference's `*` computes the integer multiple s*P with a 252-step double-and-add; any
+// algorithm that returns the same group element gives an equal point under its projective `==`
+// (/root/reference/tests/keys.rs:52-58), so the schedules here are free to differ:
+//   * variable base  : signed fixed windows (regular recoding, identical control flow in all 32
+//                      lanes -- a wNAF's data-dependent add positions would diverge per lane);
+//   * fixed base G/G': comb of 8-bit signed windows, 32 mixed additions and no doublings.
+#pragma once
+#include "fq.cuh"
+
+namespace sb200 {
+
+struct proj {  // (X : Y : Z), x = X/Z, y = Y/Z
+  fq X, Y, Z;
+};
+struct ext {  // extended: T = X*Y/Z
+  fq X, Y, Z, T;
+};
+struct p1p1 {  // completed point: X = E*F, Y = G*H, Z = F*G, T = E*H
+  fq E, F, G, H;
+};
+struct pniels {  // projective Niels form of a point: (Y+X, Y-X, Z, 2d*T)
+  fq YpX, YmX, Z, T2d;
+};
+struct aniels {  // affine Niels form (Z = 1): (y+x, y-x, 2d*x*y)
+  fq YpX, YmX, T2d;
+};
+
+SB_HD fq ed_2d() {
+  const fq c = {SB200_ED_2D_INIT};
+  return c;
+}
+SB_HD fq ed_d() {
+  const fq c = {SB200_ED_D_INIT};
+  return c;
+}
+
+SB_HD ext ext_identity() {
+  ext r;
+  r.X = fq_zero();
+  r.Y = fq_one();
+  r.Z = fq_one();
+  r.T = fq_zero();
+  return r;
+}
+
+SB_HD proj p1p1_to_proj(const p1p1& c) {
+  proj r;
+  r.X = fq_mul(c.E, c.F);
+  r.Y = fq_mul(c.G, c.H);
+  r.Z = fq_mul(c.F, c.G);
+  return r;
+}
+SB_HD ext p1p1_to_ext(const p1p1& c) {
+  ext r;
+  r.X = fq_mul(c.E, c.F);
+  r.Y = fq_mul(c.G, c.H);
+  r.Z = fq_mul(c.F, c.G);
+  r.T = fq_mul(c.E, c.H);
+  return r;
+}
+
+// 2P, 4 squarings (dbl-2008-hwcd with a = -1, signs arranged so H = A + B, F = C - G)
+SB_HD p1p1 ed_dbl(const fq& X, const fq& Y, const fq& Z) {
+  fq A = fq_sqr(X);
+  fq B = fq_sqr(Y);
+  fq C = fq_dbl(fq_sqr(Z));
+  fq S = fq_sqr(fq_add(X, Y));
+  p1p1 r;
+  r.H = fq_add(A, B);
+  r.G = fq_sub(B, A);
+  r.E = fq_sub(S, r.H);
+  r.F = fq_sub(C, r.G);
+  return r;
+}
+
+// P + Q, Q in projective Niels form: 4 multiplications (add-2008-hwcd-3, k = 2d)
+SB_HD p1p1 ed_add(const ext& p, const pniels& q) {
+  fq A = fq_mul(fq_sub(p.Y, p.X), q.YmX);
+  fq B = fq_mul(fq_add(p.Y, p.X), q.YpX);
+  fq C = fq_mul(p.T, q.T2d);
+  fq D = fq_dbl(fq_mul(p.Z, q.Z));
+  p1p1 r;
+  r.E = fq_sub(B, A);
+  r.F = fq_sub(D, C);
+  r.G = fq_add(D, C);
+  r.H = fq_add(B, A);
+  return r;
+}
+
+// P + Q, Q affine Niels: 3 multiplications
+SB_HD p1p1 ed_add(const ext& p, const aniels& q) {
+  fq A = fq_mul(fq_sub(p.Y, p.X), q.YmX);
+  fq B = fq_mul(fq_add(p.Y, p.X), q.YpX);
+  fq C = fq_mul(p.T, q.T2d);
+  fq D = fq_dbl(p.Z);
+  p1p1 r;
+  r.E = fq_sub(B, A);
+  r.F = fq_sub(D, C);
+  r.G = fq_add(D, C);
+  r.H = fq_add(B, A);
+  return r;
+}
+
+SB_HD pniels ext_to_pniels(const ext& p) {
+  pniels r;
+  r.YpX = fq_add(p.Y, p.X);
+  r.YmX = fq_sub(p.Y, p.X);
+  r.Z = p.Z;
+  r.T2d = fq_mul(p.T, ed_2d());
+  return r;
+}
+
+SB_HD pniels pniels_identity() {
+  pniels r;
+  r.YpX = fq_one();
+  r.YmX = fq_one();
+  r.Z = fq_one();
+  r.T2d = fq_zero();
+  return r;
+}
+
+// -Q:  swap (Y+X, Y-X), negate 2dT.  Branch-free select.
+SB_HD pniels pniels_cneg(const pniels& q, bool neg) {
+  pniels r;
+  r.YpX = fq_select(q.YpX, q.YmX, neg);
+  r.YmX = fq_select(q.YmX, q.YpX, neg);
+  r.Z = q.Z;
+  r.T2d = fq_select(q.T2d, fq_neg(q.T2d), neg);
+  return r;
+}
+SB_HD aniels aniels_cneg(const aniels& q, bool neg) {
+  aniels r;
+  r.YpX = fq_select(q.YpX, q.YmX, neg);
+  r.YmX = fq_select(q.YmX, q.YpX, neg);
+  r.T2d = fq_select(q.T2d, fq_neg(q.T2d), neg);
+  return r;
+}
+
+// (U : V : Z) with Z != 0  ->  extended (U*Z : V*Z : Z^2 : U*V)
+SB_HD ext proj_to_ext(const fq& U, const fq& V, const fq& Z) {
+  ext r;
+  r.X = fq_mul(U, Z);
+  r.Y = fq_mul(V, Z);
+  r.Z = fq_sqr(Z);
+  r.T = fq_mul(U, V);
+  return r;
+}
+SB_HD ext affine_to_ext(const fq& u, const fq& v) {
+  ext r;
+  r.X = u;
+  r.Y = v;
+  r.Z = fq_one();
+  r.T = fq_mul(u, v);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// scalar recoding.  k (canonical, 8 x u32 LE) + "all halves" offset; window i of the sum minus
+// 2^(W-1) is the signed digit, so no carries are needed when walking windows MSB-first.
+// ------------------------------------------------------------------------------------------
+template <int W>
+SB_HD void recode_offset(uint32_t* k) {  // k += sum_i 2^(W-1) * 2^(W*i) over all windows that fit in 256 bits
+  static_assert(W == 4 || W == 8, "window widths that tile 32-bit limbs");
+  const uint32_t c = (W == 4) ? 0x88888888u : 0x80808080u;
+  const uint32_t off[8] = {c, c, c, c, c, c, c, c};
+  add8(k, k, off);  // k < 2^252 => no carry out
+}
+template <int W>
+SB_HD int recode_digit(const uint32_t* k, int i) {  // signed digit of window i, in [-2^(W-1), 2^(W-1))
+  const int per = 32 / W;
+  uint32_t w = (k[i / per] >> ((i % per) * W)) & ((1u << W) - 1u);
+  return (int)w - (1 << (W - 1));
+}
+
+// ------------------------------------------------------------------------------------------
+// variable-base:  acc = k * P, k < 2^252 given already offset-recoded for W = 4 (64 windows; digits
+// in [-8, 7]).  `tab` holds 0P..8P in projective Niels form (9 entries, thread-private).
+// `nwin` windows are processed (63 is enough for a challenge c < 2^250, 64 for any k < 2^252).
+// Returns the completed form of the last addition.
+// ------------------------------------------------------------------------------------------
+SB_HD void vartable_build(pniels* tab, const ext& P) {
+  tab[0] = pniels_identity();
+  tab[1] = ext_to_pniels(P);
+  ext cur = P;
+#pragma unroll 1
+  for (int i = 2; i <= 8; i++) {
+    cur = p1p1_to_ext(ed_add(cur, tab[1]));
+    tab[i] = ext_to_pniels(cur);
+  }
+}
+
+SB_HD pniels vartable_lookup(const pniels* tab, int d) {
+  bool neg = d < 0;
+  int idx = neg ? -d : d;
+  return pniels_cneg(tab[idx], neg);
+}
+
+SB_HD p1p1 ed_mul_var(const pniels* tab, const uint32_t* k_rec, int nwin) {
+  // top window: acc = digit * P directly (identity + entry)
+  p1p1 c = ed_add(ext_identity(), vartable_lookup(tab, recode_digit<4>(k_rec, nwin - 1)));
+#pragma unroll 1
+  for (int i = nwin - 2; i >= 0; i--) {
+    proj p = p1p1_to_proj(c);
+    c = ed_dbl(p.X, p.Y, p.Z);
+    p = p1p1_to_proj(c);
+    c = ed_dbl(p.X, p.Y, p.Z);
+    p = p1p1_to_proj(c);
+    c = ed_dbl(p.X, p.Y, p.Z);
+    p = p1p1_to_proj(c);
+    c = ed_dbl(p.X, p.Y, p.Z);
+    ext e = p1p1_to_ext(c);
+    c = ed_add(e, vartable_lookup(tab, recode_digit<4>(k_rec, i)));
+  }
+  return c;
+}
+
+// Straus: k1*P1 + k2*P2 with shared doublings (variable-generator verification,
+// /root/reference/src/keys/public.rs:411-412).
+SB_HD p1p1 ed_mul_var2(const pniels* tab1, const uint32_t* k1_rec, const pniels* tab2, const uint32_t* k2_rec, int nwin) {
+  p1p1 c = ed_add(ext_identity(), vartable_lookup(tab1, recode_digit<4>(k1_rec, nwin - 1)));
+  c = ed_add(p1p1_to_ext(c), vartable_lookup(tab2, recode_digit<4>(k2_rec, nwin - 1)));
+#pragma unroll 1
+  for (int i = nwin - 2; i >= 0; i--) {
+    proj p = p1p1_to_proj(c);
+    c = ed_dbl(p.X, p.Y, p.Z);
+    p = p1p1_to_proj(c);
+    c = ed_dbl(p.X, p.Y, p.Z);
+    p = p1p1_to_proj(c);
+    c = ed_dbl(p.X, p.Y, p.Z);
+    p = p1p1_to_proj(c);
+    c = ed_dbl(p.X, p.Y, p.Z);
+    ext e = p1p1_to_ext(c);
+    c = ed_add(e, vartable_lookup(tab1, recode_digit<4>(k1_rec, i)));
+    e = p1p1_to_ext(c);
+    c = ed_add(e, vartable_lookup(tab2, recode_digit<4>(k2_rec, i)));
+  }
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------
+// fixed-base comb.  Table layout: window j (0..31), entry e (0..128) = e * 256^j * B in affine Niels
+// form, entry 0 = identity; 129 * 32 entries of 96 bytes.  acc += k * B with k offset-recoded (W = 8).
+// ------------------------------------------------------------------------------------------
+constexpr int COMB_WINDOWS = 32;
+constexpr int COMB_ENTRIES = 129;
+
+SB_HD aniels comb_load(const uint32_t* table, int j, int e) {
+  const uint4* p = reinterpret_cast<const uint4*>(table) + (size_t)(j * COMB_ENTRIES + e) * 6;
+  uint4 q0 = p[0], q1 = p[1], q2 = p[2], q3 = p[3], q4 = p[4], q5 = p[5];
+  aniels r;
+  r.YpX = {{q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w}};
+  r.YmX = {{q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w}};
+  r.T2d = {{q4.x, q4.y, q4.z, q4.w, q5.x, q5.y, q5.z, q5.w}};
+  return r;
+}
+
+// acc (extended) += k*B ; returns completed form of the last addition (use p1p1_to_ext / compare).
+SB_HD p1p1 ed_comb_add(ext acc, const uint32_t* table, const uint32_t* k_rec) {
+  p1p1 c;
+#pragma unroll 1
+  for (int j = 0; j < COMB_WINDOWS; j++) {
+    int d = recode_digit<8>(k_rec, j);
+    bool neg = d < 0;
+    aniels n = aniels_cneg(comb_load(table, j, neg ? -d : d), neg);
+    c = ed_add(acc, n);
+    if (j + 1 < COMB_WINDOWS) acc = p1p1_to_ext(c);
+  }
+  return c;
+}
+
+}  // namespace sb200
+
+namespace sb200 {
+
+// One comb-table entry: e * 256^j * B in affine Niels form (entry 0 = identity), written as 24 limbs.
+// Run once per (j, e) at context creation (init kernel) -- plain double-and-add, speed irrelevant.
+SB_HD void comb_build_entry(const fq& Bu, const fq& Bv, int j, int e, uint32_t* out24) {
+  ext base = affine_to_ext(Bu, Bv);
+  pniels nb = ext_to_pniels(base);
+  ext acc = ext_identity();
+  // scalar = e << (8*j); walk its bits MSB-first: bits 8*j+7 .. 0
+#pragma unroll 1
+  for (int bit = 8 * j + 7; bit >= 0; bit--) {
+    acc = p1p1_to_ext(ed_dbl(acc.X, acc.Y, acc.Z));
+    int eb = bit - 8 * j;
+    bool set = (eb >= 0) && ((e >> eb) & 1);
+    ext sum = p1p1_to_ext(ed_add(acc, nb));
+    acc.X = fq_select(acc.X, sum.X, set);
+    acc.Y = fq_select(acc.Y, sum.Y, set);
+    acc.Z = fq_select(acc.Z, sum.Z, set);
+    acc.T = fq_select(acc.T, sum.T, set);
+  }
+  fq zi = fq_inv(acc.Z);
+  fq x = fq_mul(acc.X, zi), y = fq_mul(acc.Y, zi);
+  fq ypx = fq_add(y, x), ymx = fq_sub(y, x), t2d = fq_mul(fq_mul(x, y), ed_2d());
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    out24[i] = ypx.v[i];
+    out24[8 + i] = ymx.v[i];
+    out24[16 + i] = t2d.v[i];
+  }
+}
+
+}  // namespace sb200

@@ -1,0 +1,451 @@
+// 255-bit Montgomery arithmetic on 8 x 32-bit limbs for sm_100a.
+//
+//   Fq  = BLS12-381 scalar field  (dusk_bls12_381::BlsScalar; JubJub's base field)
+//   Fr  = JubJub scalar field     (dusk_jubjub::JubJubScalar)
+//
+// Replaces the arithmetic the reference reaches through `BlsScalar`/`JubJubScalar` operators at
+// every call site of /root/reference/src/keys/public.rs:121-130 and
+// /root/reference/src/keys/secret.rs:150-168.
+//
+// The multiplier is an interleaved (CIOS-style) Montgomery product built from carry chains of
+// `mad.lo.cc.u32 / madc.hi.cc.u32` pairs, which ptxas fuses into IMAD.WIDE.U32(.X) with the carry
+// in a predicate.  The running value lives in two register arrays X (64-bit pairs aligned to even
+// limb positions) and Y (pairs aligned to odd positions) so every pair keeps the same two
+// registers for the whole product (no MOV traffic); the per-row right shift by one limb swaps the
+// roles of X and Y.  q = 1 (mod 2^32) makes the Montgomery factor m = -t0 (no multiply) and
+// q[1] = 2^32 - 1 turns two more columns of the reduction into adds: 8 + 6 wide multiplies / row.
+//
+// Every chain is one asm block on the device and one emulation routine on the host, so the row
+// structure (folds, shifts, carries) is unit-tested on the CPU as well (tests/host_arith_test.cpp);
+// the host build is test scaffolding and is never linked into the product library's compute path.
+#pragma once
+#include <cstdint>
+
+#include "constants_gen.cuh"
+
+#if defined(__CUDACC__)
+#define SB_HD __host__ __device__ __forceinline__
+#define SB_D __device__ __forceinline__
+#else
+#define SB_HD inline
+#define SB_D inline
+#endif
+
+namespace sb200 {
+
+struct fq {
+  uint32_t v[8];
+};
+
+// ------------------------------------------------------------------------------------------
+// carry-chain blocks
+// ------------------------------------------------------------------------------------------
+#if !defined(__CUDA_ARCH__)
+namespace emu {
+// acc[0..n) += addend (little-endian limbs) starting at limb `at`; returns carry out of limb n-1
+static inline uint32_t add_at(uint32_t* acc, int n, int at, uint64_t val, uint32_t cin) {
+  unsigned __int128 carry = cin;
+  for (int i = at; i < n; i++) {
+    unsigned __int128 t = (unsigned __int128)acc[i] + carry;
+    if (i == at) t += (uint32_t)val;
+    if (i == at + 1) t += (uint32_t)(val >> 32);
+    acc[i] = (uint32_t)t;
+    carry = t >> 32;
+  }
+  return (uint32_t)carry;
+}
+}  // namespace emu
+#endif
+
+// Block A:  x0 += xf (fold of the limb that fell off the even array), carry goes into the odd chain;
+//           y[0..7] += a * (b1, b3, b5, b7).  No carry out of y[7] (the running value fits 9 limbs).
+SB_HD void blk_fold_mac_odd(uint32_t& x0, uint32_t xf, uint32_t* y, uint32_t a, uint32_t b1, uint32_t b3,
+                            uint32_t b5, uint32_t b7) {
+#if defined(__CUDA_ARCH__)
+  asm("add.cc.u32 %0, %0, %9;\n\t"
+      "madc.lo.cc.u32 %1, %10, %11, %1;\n\t"
+      "madc.hi.cc.u32 %2, %10, %11, %2;\n\t"
+      "madc.lo.cc.u32 %3, %10, %12, %3;\n\t"
+      "madc.hi.cc.u32 %4, %10, %12, %4;\n\t"
+      "madc.lo.cc.u32 %5, %10, %13, %5;\n\t"
+      "madc.hi.cc.u32 %6, %10, %13, %6;\n\t"
+      "madc.lo.cc.u32 %7, %10, %14, %7;\n\t"
+      "madc.hi.u32 %8, %10, %14, %8;"
+      : "+r"(x0), "+r"(y[0]), "+r"(y[1]), "+r"(y[2]), "+r"(y[3]), "+r"(y[4]), "+r"(y[5]), "+r"(y[6]), "+r"(y[7])
+      : "r"(xf), "r"(a), "r"(b1), "r"(b3), "r"(b5), "r"(b7));
+#else
+  uint64_t t = (uint64_t)x0 + xf;
+  x0 = (uint32_t)t;
+  uint32_t c = (uint32_t)(t >> 32);
+  c = emu::add_at(y, 8, 0, (uint64_t)a * b1, c);
+  c += emu::add_at(y, 8, 2, (uint64_t)a * b3, 0);
+  c += emu::add_at(y, 8, 4, (uint64_t)a * b5, 0);
+  c += emu::add_at(y, 8, 6, (uint64_t)a * b7, 0);
+  (void)c;
+#endif
+}
+
+// Block B:  x[0..7] += a * (b0, b2, b4, b6); the carry out of x[7] (limb position 8) is added to ytop
+//           (= y[7], the odd array's register for position 8).
+SB_HD void blk_mac_even(uint32_t* x, uint32_t& ytop, uint32_t a, uint32_t b0, uint32_t b2, uint32_t b4, uint32_t b6) {
+#if defined(__CUDA_ARCH__)
+  asm("mad.lo.cc.u32 %0, %9, %10, %0;\n\t"
+      "madc.hi.cc.u32 %1, %9, %10, %1;\n\t"
+      "madc.lo.cc.u32 %2, %9, %11, %2;\n\t"
+      "madc.hi.cc.u32 %3, %9, %11, %3;\n\t"
+      "madc.lo.cc.u32 %4, %9, %12, %4;\n\t"
+      "madc.hi.cc.u32 %5, %9, %12, %5;\n\t"
+      "madc.lo.cc.u32 %6, %9, %13, %6;\n\t"
+      "madc.hi.cc.u32 %7, %9, %13, %7;\n\t"
+      "addc.u32 %8, %8, 0;"
+      : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]), "+r"(ytop)
+      : "r"(a), "r"(b0), "r"(b2), "r"(b4), "r"(b6));
+#else
+  uint32_t c = emu::add_at(x, 8, 0, (uint64_t)a * b0, 0);
+  c += emu::add_at(x, 8, 2, (uint64_t)a * b2, 0);
+  c += emu::add_at(x, 8, 4, (uint64_t)a * b4, 0);
+  c += emu::add_at(x, 8, 6, (uint64_t)a * b6, 0);
+  ytop += c;
+#endif
+}
+
+// Generic reduction blocks (any odd modulus p with limbs p0..p7): x += m * (p0,p2,p4,p6), y += m * (p1,p3,p5,p7)
+SB_HD void blk_mac_odd(uint32_t* y, uint32_t a, uint32_t b1, uint32_t b3, uint32_t b5, uint32_t b7) {
+#if defined(__CUDA_ARCH__)
+  asm("mad.lo.cc.u32 %0, %8, %9, %0;\n\t"
+      "madc.hi.cc.u32 %1, %8, %9, %1;\n\t"
+      "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+      "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+      "madc.lo.cc.u32 %4, %8, %11, %4;\n\t"
+      "madc.hi.cc.u32 %5, %8, %11, %5;\n\t"
+      "madc.lo.cc.u32 %6, %8, %12, %6;\n\t"
+      "madc.hi.u32 %7, %8, %12, %7;"
+      : "+r"(y[0]), "+r"(y[1]), "+r"(y[2]), "+r"(y[3]), "+r"(y[4]), "+r"(y[5]), "+r"(y[6]), "+r"(y[7])
+      : "r"(a), "r"(b1), "r"(b3), "r"(b5), "r"(b7));
+#else
+  uint32_t c = emu::add_at(y, 8, 0, (uint64_t)a * b1, 0);
+  c += emu::add_at(y, 8, 2, (uint64_t)a * b3, 0);
+  c += emu::add_at(y, 8, 4, (uint64_t)a * b5, 0);
+  c += emu::add_at(y, 8, 6, (uint64_t)a * b7, 0);
+  (void)c;
+#endif
+}
+
+// Fq-specific reduction, even half:  x += m * (1, q2, q4, q6) with m = -x0  =>  x0 becomes 0 and the
+// carry into x1 is (x0 != 0).  Carry out of x[7] goes to ytop.
+SB_HD void blk_red_even_q(uint32_t* x, uint32_t& ytop, uint32_t m, uint32_t q2, uint32_t q4, uint32_t q6) {
+#if defined(__CUDA_ARCH__)
+  asm("add.cc.u32 %0, %0, %9;\n\t"
+      "addc.cc.u32 %1, %1, 0;\n\t"
+      "madc.lo.cc.u32 %2, %9, %10, %2;\n\t"
+      "madc.hi.cc.u32 %3, %9, %10, %3;\n\t"
+      "madc.lo.cc.u32 %4, %9, %11, %4;\n\t"
+      "madc.hi.cc.u32 %5, %9, %11, %5;\n\t"
+      "madc.lo.cc.u32 %6, %9, %12, %6;\n\t"
+      "madc.hi.cc.u32 %7, %9, %12, %7;\n\t"
+      "addc.u32 %8, %8, 0;"
+      : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]), "+r"(ytop)
+      : "r"(m), "r"(q2), "r"(q4), "r"(q6));
+#else
+  uint32_t c = emu::add_at(x, 8, 0, (uint64_t)m, 0);
+  c += emu::add_at(x, 8, 2, (uint64_t)m * q2, 0);
+  c += emu::add_at(x, 8, 4, (uint64_t)m * q4, 0);
+  c += emu::add_at(x, 8, 6, (uint64_t)m * q6, 0);
+  ytop += c;
+#endif
+}
+
+// Fq-specific reduction, odd half:  y += m * (q1, q3, q5, q7), q1 = 2^32 - 1, so the first product is
+// (lo, hi) = (t0, m - (t0 != 0)) with t0 = -m = the limb being cancelled; passed in precomputed.
+SB_HD void blk_red_odd_q(uint32_t* y, uint32_t m, uint32_t lo1, uint32_t hi1, uint32_t q3, uint32_t q5, uint32_t q7) {
+#if defined(__CUDA_ARCH__)
+  asm("add.cc.u32 %0, %0, %9;\n\t"
+      "addc.cc.u32 %1, %1, %10;\n\t"
+      "madc.lo.cc.u32 %2, %8, %11, %2;\n\t"
+      "madc.hi.cc.u32 %3, %8, %11, %3;\n\t"
+      "madc.lo.cc.u32 %4, %8, %12, %4;\n\t"
+      "madc.hi.cc.u32 %5, %8, %12, %5;\n\t"
+      "madc.lo.cc.u32 %6, %8, %13, %6;\n\t"
+      "madc.hi.u32 %7, %8, %13, %7;"
+      : "+r"(y[0]), "+r"(y[1]), "+r"(y[2]), "+r"(y[3]), "+r"(y[4]), "+r"(y[5]), "+r"(y[6]), "+r"(y[7])
+      : "r"(m), "r"(lo1), "r"(hi1), "r"(q3), "r"(q5), "r"(q7));
+#else
+  uint32_t c = emu::add_at(y, 8, 0, ((uint64_t)hi1 << 32) | lo1, 0);
+  c += emu::add_at(y, 8, 2, (uint64_t)m * q3, 0);
+  c += emu::add_at(y, 8, 4, (uint64_t)m * q5, 0);
+  c += emu::add_at(y, 8, 6, (uint64_t)m * q7, 0);
+  (void)c;
+#endif
+}
+
+// r = a + b (8 limbs), returns carry
+SB_HD uint32_t add8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  uint32_t c;
+#if defined(__CUDA_ARCH__)
+  asm("add.cc.u32 %0, %9, %17;\n\t"
+      "addc.cc.u32 %1, %10, %18;\n\t"
+      "addc.cc.u32 %2, %11, %19;\n\t"
+      "addc.cc.u32 %3, %12, %20;\n\t"
+      "addc.cc.u32 %4, %13, %21;\n\t"
+      "addc.cc.u32 %5, %14, %22;\n\t"
+      "addc.cc.u32 %6, %15, %23;\n\t"
+      "addc.cc.u32 %7, %16, %24;\n\t"
+      "addc.u32 %8, 0, 0;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]),
+        "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
+  uint64_t t = 0;
+  for (int i = 0; i < 8; i++) {
+    t += (uint64_t)a[i] + b[i];
+    r[i] = (uint32_t)t;
+    t >>= 32;
+  }
+  c = (uint32_t)t;
+#endif
+  return c;
+}
+
+// r = a - b (8 limbs), returns borrow mask (0 or 0xffffffff)
+SB_HD uint32_t sub8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  uint32_t c;
+#if defined(__CUDA_ARCH__)
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]),
+        "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
+  int64_t t = 0;
+  for (int i = 0; i < 8; i++) {
+    t += (int64_t)a[i] - (int64_t)b[i];
+    r[i] = (uint32_t)t;
+    t >>= 32;  // arithmetic shift keeps the borrow as -1
+  }
+  c = (uint32_t)t;
+#endif
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------
+// moduli
+// ------------------------------------------------------------------------------------------
+struct FqP {
+  static SB_HD constexpr uint32_t p(int i) {
+    constexpr uint32_t t[8] = SB200_FQ_MOD_INIT;
+    return t[i];
+  }
+};
+struct FrP {
+  static SB_HD constexpr uint32_t p(int i) {
+    constexpr uint32_t t[8] = SB200_FR_MOD_INIT;
+    return t[i];
+  }
+  static constexpr uint32_t ninv = SB200_FR_NINV;
+};
+
+template <class P>
+SB_HD void cond_sub_p(uint32_t* r) {  // r in [0, 2p) -> [0, p)
+  uint32_t t[8];
+  const uint32_t pp[8] = {P::p(0), P::p(1), P::p(2), P::p(3), P::p(4), P::p(5), P::p(6), P::p(7)};
+  uint32_t borrow = sub8(t, r, pp);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = borrow ? r[i] : t[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// Fq
+// ------------------------------------------------------------------------------------------
+SB_HD fq fq_zero() {
+  fq r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = 0;
+  return r;
+}
+SB_HD fq fq_one() {  // Montgomery 1
+  const uint32_t c[8] = SB200_FQ_ONE_INIT;
+  fq r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = c[i];
+  return r;
+}
+
+SB_HD fq fq_add(const fq& a, const fq& b) {
+  fq r;
+  add8(r.v, a.v, b.v);  // a + b < 2q < 2^256: no carry
+  cond_sub_p<FqP>(r.v);
+  return r;
+}
+
+SB_HD fq fq_sub(const fq& a, const fq& b) {
+  fq r;
+  uint32_t borrow = sub8(r.v, a.v, b.v);
+  uint32_t t[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) t[i] = FqP::p(i) & borrow;
+  add8(r.v, r.v, t);
+  return r;
+}
+
+SB_HD fq fq_neg(const fq& a) { return fq_sub(fq_zero(), a); }
+
+SB_HD fq fq_dbl(const fq& a) { return fq_add(a, a); }
+
+SB_HD bool fq_is_zero(const fq& a) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) o |= a.v[i];
+  return o == 0;
+}
+
+SB_HD bool fq_eq(const fq& a, const fq& b) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) o |= a.v[i] ^ b.v[i];
+  return o == 0;
+}
+
+SB_HD fq fq_select(const fq& a, const fq& b, bool take_b) {
+  fq r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = take_b ? b.v[i] : a.v[i];
+  return r;
+}
+
+// Montgomery product a * b * 2^-256 mod q, inputs and output canonical (< q).
+SB_HD fq fq_mul(const fq& a, const fq& b) {
+  uint32_t X[8], Y[8], xf = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) X[i] = Y[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint32_t ai = a.v[i];
+    blk_fold_mac_odd(X[0], xf, Y, ai, b.v[1], b.v[3], b.v[5], b.v[7]);
+    blk_mac_even(X, Y[7], ai, b.v[0], b.v[2], b.v[4], b.v[6]);
+    uint32_t t0 = X[0];
+    uint32_t m = 0u - t0;
+    uint32_t hi1 = m - (t0 != 0 ? 1u : 0u);
+    blk_red_even_q(X, Y[7], m, FqP::p(2), FqP::p(4), FqP::p(6));
+    blk_red_odd_q(Y, m, t0, hi1, FqP::p(3), FqP::p(5), FqP::p(7));
+    // divide by 2^32: the odd array becomes the even one; X[1] is folded in at the next row
+    xf = X[1];
+    uint32_t nx[8], ny[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) nx[k] = Y[k];
+#pragma unroll
+    for (int k = 0; k < 6; k++) ny[k] = X[k + 2];
+    ny[6] = 0;
+    ny[7] = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      X[k] = nx[k];
+      Y[k] = ny[k];
+    }
+  }
+  // value = X + xf + (Y << 32)  (< 2q)
+  fq r;
+  uint32_t s[8] = {xf, Y[0], Y[1], Y[2], Y[3], Y[4], Y[5], Y[6]};
+  add8(r.v, X, s);
+  cond_sub_p<FqP>(r.v);
+  return r;
+}
+
+SB_HD fq fq_sqr(const fq& a) { return fq_mul(a, a); }
+
+SB_HD fq fq_to_mont(const fq& a) {
+  const fq r2 = {SB200_FQ_R2_INIT};
+  return fq_mul(a, r2);
+}
+SB_HD fq fq_from_mont(const fq& a) {
+  fq one = fq_zero();
+  one.v[0] = 1;
+  return fq_mul(a, one);
+}
+
+// a^(q-2): 4-bit fixed windows over the constant exponent (255 squarings + 64 + 14 multiplies).
+SB_HD fq fq_inv(const fq& a) {
+  fq tab[16];
+  tab[0] = fq_one();
+  tab[1] = a;
+#pragma unroll 1
+  for (int i = 2; i < 16; i++) tab[i] = fq_mul(tab[i - 1], a);
+  // q - 2, little-endian limbs
+  const uint32_t e[8] = {0xffffffffu, 0xfffffffeu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+  fq acc = fq_one();
+#pragma unroll 1
+  for (int w = 63; w >= 0; w--) {
+    acc = fq_sqr(acc);
+    acc = fq_sqr(acc);
+    acc = fq_sqr(acc);
+    acc = fq_sqr(acc);
+    uint32_t d = (e[w >> 3] >> ((w & 7) * 4)) & 15u;
+    acc = fq_mul(acc, tab[d]);
+  }
+  return acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fr (generic Montgomery; only u = r - c*sk needs it: one product + one subtraction per signature,
+// /root/reference/src/keys/secret.rs:165,237,448)
+// ------------------------------------------------------------------------------------------
+struct fr {
+  uint32_t v[8];
+};
+
+SB_HD fr fr_mont_mul(const fr& a, const fr& b) {
+  uint32_t X[8], Y[8], xf = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) X[i] = Y[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint32_t ai = a.v[i];
+    blk_fold_mac_odd(X[0], xf, Y, ai, b.v[1], b.v[3], b.v[5], b.v[7]);
+    blk_mac_even(X, Y[7], ai, b.v[0], b.v[2], b.v[4], b.v[6]);
+    uint32_t m = X[0] * FrP::ninv;
+    blk_mac_even(X, Y[7], m, FrP::p(0), FrP::p(2), FrP::p(4), FrP::p(6));
+    blk_mac_odd(Y, m, FrP::p(1), FrP::p(3), FrP::p(5), FrP::p(7));
+    xf = X[1];
+    uint32_t nx[8], ny[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) nx[k] = Y[k];
+#pragma unroll
+    for (int k = 0; k < 6; k++) ny[k] = X[k + 2];
+    ny[6] = 0;
+    ny[7] = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      X[k] = nx[k];
+      Y[k] = ny[k];
+    }
+  }
+  fr r;
+  uint32_t s[8] = {xf, Y[0], Y[1], Y[2], Y[3], Y[4], Y[5], Y[6]};
+  add8(r.v, X, s);
+  cond_sub_p<FrP>(r.v);
+  return r;
+}
+
+// canonical a * b mod r for canonical inputs:  mont(mont(a, b), R^2) = a*b*R^-1 * R^2 * R^-1
+SB_HD fr fr_mul(const fr& a, const fr& b) {
+  const fr r2 = {SB200_FR_R2_INIT};
+  return fr_mont_mul(fr_mont_mul(a, b), r2);
+}
+
+SB_HD fr fr_sub(const fr& a, const fr& b) {
+  fr r;
+  uint32_t borrow = sub8(r.v, a.v, b.v);
+  uint32_t t[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) t[i] = FrP::p(i) & borrow;
+  add8(r.v, r.v, t);
+  return r;
+}
+
+}  // namespace sb200

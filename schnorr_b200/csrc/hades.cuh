@@ -1,0 +1,136 @@
+// Hades252 permutation (width 5, x^5, 8 full + 59 partial rounds) and the Poseidon sponge shapes the
+// Schnorr challenge uses.  Replaces `dusk_poseidon::sponge::truncated::hash` as called from
+// challenge_hash / challenge_hash_double: /root/reference/src/signatures.rs:127-134, 275-290.
+//
+// One permutation per thread, state in registers (5 x 8 limbs), constants broadcast from
+// __constant__ memory (every lane reads the same address in lock-step).
+// The 59 partial rounds run in the sparse factorisation produced by tools/gen_constants.py
+// (9 products per round instead of 25; algebraically identical, hence bit-exact); the dense form is
+// kept as hades_perm_dense for the parity tests.
+#pragma once
+#include "fq.cuh"
+
+namespace sb200 {
+
+#define SB_HADES_W 5
+
+#if defined(__CUDACC__)
+__constant__ uint32_t d_hades_rc[SB200_HADES_NRC][8] = SB200_HADES_RC_INIT;
+__constant__ uint32_t d_hades_mds[25][8] = SB200_HADES_MDS_INIT;
+__constant__ uint32_t d_hades_pre[5][8] = SB200_HADES_PRE_INIT;
+__constant__ uint32_t d_hades_sparse[59 * 11][8] = SB200_HADES_SPARSE_INIT;
+__constant__ uint32_t d_hades_post[25][8] = SB200_HADES_POST_INIT;
+#endif
+static const uint32_t h_hades_rc[SB200_HADES_NRC][8] = SB200_HADES_RC_INIT;
+static const uint32_t h_hades_mds[25][8] = SB200_HADES_MDS_INIT;
+static const uint32_t h_hades_pre[5][8] = SB200_HADES_PRE_INIT;
+static const uint32_t h_hades_sparse[59 * 11][8] = SB200_HADES_SPARSE_INIT;
+static const uint32_t h_hades_post[25][8] = SB200_HADES_POST_INIT;
+
+#if defined(__CUDA_ARCH__)
+#define SB_CONST(name) d_##name
+#else
+#define SB_CONST(name) h_##name
+#endif
+
+SB_HD fq ld8(const uint32_t* p) {
+  fq r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = p[i];
+  return r;
+}
+
+SB_HD fq fq_pow5(const fq& x) {
+  fq x2 = fq_sqr(x);
+  fq x4 = fq_sqr(x2);
+  return fq_mul(x4, x);
+}
+
+// s <- M * s with M a dense 5x5 matrix in constant memory (row-major)
+#define SB_MATMUL5(s, mat)                                              \
+  do {                                                                  \
+    fq _r[5];                                                           \
+    _Pragma("unroll 1") for (int _k = 0; _k < 5; _k++) {                \
+      fq _a = fq_mul(ld8(SB_CONST(mat)[_k * 5]), s[0]);                 \
+      _Pragma("unroll") for (int _j = 1; _j < 5; _j++)                  \
+          _a = fq_add(_a, fq_mul(ld8(SB_CONST(mat)[_k * 5 + _j]), s[_j])); \
+      _r[_k] = _a;                                                      \
+    }                                                                   \
+    _Pragma("unroll") for (int _k = 0; _k < 5; _k++) s[_k] = _r[_k];    \
+  } while (0)
+
+SB_HD void hades_full_round(fq* s, int rc_base) {
+#pragma unroll
+  for (int k = 0; k < 5; k++) s[k] = fq_pow5(fq_add(s[k], ld8(SB_CONST(hades_rc)[rc_base + k])));
+  SB_MATMUL5(s, hades_mds);
+}
+
+// Reference-shaped permutation (ScalarStrategy::perm of dusk-hades): used by parity tests.
+SB_HD void hades_perm_dense(fq* s) {
+  int rc = 0;
+#pragma unroll 1
+  for (int r = 0; r < 4; r++, rc += 5) hades_full_round(s, rc);
+#pragma unroll 1
+  for (int r = 0; r < 59; r++, rc += 5) {
+#pragma unroll
+    for (int k = 0; k < 5; k++) s[k] = fq_add(s[k], ld8(SB_CONST(hades_rc)[rc + k]));
+    s[4] = fq_pow5(s[4]);
+    SB_MATMUL5(s, hades_mds);
+  }
+#pragma unroll 1
+  for (int r = 0; r < 4; r++, rc += 5) hades_full_round(s, rc);
+}
+
+// Production permutation: sparse partial rounds.
+SB_HD void hades_perm(fq* s) {
+  int rc = 0;
+#pragma unroll 1
+  for (int r = 0; r < 4; r++, rc += 5) hades_full_round(s, rc);
+#pragma unroll
+  for (int k = 0; k < 4; k++) s[k] = fq_add(s[k], ld8(SB_CONST(hades_pre)[k]));
+#pragma unroll 1
+  for (int t = 0; t < 59; t++) {
+    const uint32_t(*c)[8] = &SB_CONST(hades_sparse)[t * 11];
+    s[4] = fq_pow5(fq_add(s[4], ld8(c[0])));
+    fq np = fq_mul(ld8(c[1 + 4]), s[4]);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      np = fq_add(np, fq_mul(ld8(c[1 + j]), s[j]));
+      s[j] = fq_add(s[j], fq_mul(ld8(c[6 + j]), s[4]));
+    }
+    s[4] = np;
+  }
+  SB_MATMUL5(s, hades_post);
+  rc += 59 * 5;
+#pragma unroll 1
+  for (int r = 0; r < 4; r++, rc += 5) hades_full_round(s, rc);
+}
+
+// low 250 bits of the canonical integer (dusk_poseidon::sponge::truncated), as a scalar
+SB_HD void truncate250(const fq& mont_word, uint32_t* c) {
+  fq x = fq_from_mont(mont_word);
+#pragma unroll
+  for (int i = 0; i < 8; i++) c[i] = x.v[i];
+  c[7] &= 0x03ffffffu;
+}
+
+// c = H(Ru, Rv, m): sponge state [0, Ru, Rv, m, 1], one permutation, word 1.
+template <bool DENSE = false>
+SB_HD void challenge3(const fq& Ru, const fq& Rv, const fq& m, uint32_t* c) {
+  fq s[5] = {fq_zero(), Ru, Rv, m, fq_one()};
+  if (DENSE) hades_perm_dense(s); else hades_perm(s);
+  truncate250(s[1], c);
+}
+
+// c = H(Ru, Rv, R'u, R'v, m): [0, Ru, Rv, R'u, R'v] -> perm -> word1 += m, word2 += 1 -> perm -> word 1.
+template <bool DENSE = false>
+SB_HD void challenge5(const fq& Ru, const fq& Rv, const fq& Rpu, const fq& Rpv, const fq& m, uint32_t* c) {
+  fq s[5] = {fq_zero(), Ru, Rv, Rpu, Rpv};
+  if (DENSE) hades_perm_dense(s); else hades_perm(s);
+  s[1] = fq_add(s[1], m);
+  s[2] = fq_add(s[2], fq_one());
+  if (DENSE) hades_perm_dense(s); else hades_perm(s);
+  truncate250(s[1], c);
+}
+
+}  // namespace sb200

@@ -1,0 +1,505 @@
+// libschnorr_b200.so: sm_100a kernels + the C ABI declared in include/schnorr_b200.h.
+//
+// One tuple per thread, 128 threads per CTA.  Every kernel is integer-multiply bound (~3e5
+// IMAD.WIDE per verification against ~300 bytes of input), so the inputs are read straight from the
+// tuple-major arrays with two 128-bit loads per field element (every 32-byte sector fully used) and
+// the fixed-base comb tables stay L2-resident.  Host buffers are pipelined through two streams per
+// device in chunks (H2D / kernel / D2H overlap); tuples shard by index over the context's devices
+// with no inter-GPU traffic.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/schnorr_b200.h"
+#include "core.cuh"
+
+using namespace sb200;
+
+namespace {
+
+constexpr int TPB = 128;
+constexpr int MAX_IN = 6, MAX_OUT = 4;
+constexpr int64_t CHUNK = 1 << 18;  // tuples per pipeline stage
+
+enum Op : int {
+  OP_VERIFY = 0, OP_VERIFY_DOUBLE, OP_VERIFY_VARGEN, OP_SIGN, OP_SIGN_DOUBLE, OP_SIGN_VARGEN,
+  OP_KEYGEN, OP_KEYGEN_DOUBLE, OP_KEYGEN_VARGEN, OP_DBG_FQ, OP_DBG_FR_MUL, OP_DBG_HADES, OP_DBG_SMUL
+};
+
+struct KArgs {
+  int64_t n;
+  uint32_t flags;
+  int aux;
+  const uint32_t* in[MAX_IN];
+  uint32_t* out[MAX_OUT];
+  uint32_t* bitmap;
+  const uint32_t* combG;
+  const uint32_t* combGp;
+};
+
+__device__ __forceinline__ fq ldg_fq(const uint32_t* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  fq r = {{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+  return r;
+}
+__device__ __forceinline__ void ldg_scalar(const uint32_t* p, uint32_t* k) {
+  fq t = ldg_fq(p);
+#pragma unroll
+  for (int i = 0; i < 8; i++) k[i] = t.v[i];
+}
+__device__ __forceinline__ void stg8(uint32_t* p, const uint32_t* v) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(v[0], v[1], v[2], v[3]);
+  q[1] = make_uint4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ point_in ldg_point(const uint32_t* base, int64_t i, bool affine) {
+  point_in p;
+  const uint32_t* q = base + i * (affine ? 16 : 24);
+  p.U = ldg_fq(q);
+  p.V = ldg_fq(q + 8);
+  p.Z = affine ? fq_one() : ldg_fq(q + 16);
+  p.affine = affine;
+  return p;
+}
+__device__ __forceinline__ void stg_point(uint32_t* base, int64_t i, const fq& u, const fq& v) {
+  stg8(base + i * 16, u.v);
+  stg8(base + i * 16 + 8, v.v);
+}
+
+template <int OP>
+__global__ void __launch_bounds__(TPB) k_run(const KArgs a) {
+  int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  const bool active = i < a.n;
+  if (!active) i = a.n - 1;  // idle lanes redo the last tuple so the warp stays converged
+  const bool aff = (a.flags & SB200_POINTS_AFFINE) != 0;
+  uint32_t c[8];
+
+  if (OP == OP_VERIFY || OP == OP_VERIFY_DOUBLE || OP == OP_VERIFY_VARGEN) {
+    bool ok;
+    if (OP == OP_VERIFY) {  // in: pk, u, R, m
+      uint32_t u[8];
+      ldg_scalar(a.in[1] + i * 8, u);
+      ok = verify_core(ldg_point(a.in[0], i, aff), u, ldg_point(a.in[2], i, aff), ldg_fq(a.in[3] + i * 8), a.combG, c);
+    } else if (OP == OP_VERIFY_DOUBLE) {  // in: pk, pk', u, R, R', m
+      uint32_t u[8];
+      ldg_scalar(a.in[2] + i * 8, u);
+      ok = verify_double_core(ldg_point(a.in[0], i, aff), ldg_point(a.in[1], i, aff), u, ldg_point(a.in[3], i, aff),
+                              ldg_point(a.in[4], i, aff), ldg_fq(a.in[5] + i * 8), a.combG, a.combGp, c);
+    } else {  // in: pk, gen, u, R, m
+      uint32_t u[8];
+      ldg_scalar(a.in[2] + i * 8, u);
+      ok = verify_vargen_core(ldg_point(a.in[0], i, aff), ldg_point(a.in[1], i, aff), u, ldg_point(a.in[3], i, aff),
+                              ldg_fq(a.in[4] + i * 8), c);
+    }
+    unsigned word = __ballot_sync(0xffffffffu, ok && active);
+    if ((threadIdx.x & 31) == 0 && active) a.bitmap[i >> 5] = word;
+    if (a.out[0] && active) stg8(a.out[0] + i * 8, c);
+    return;
+  }
+
+  if (OP == OP_SIGN || OP == OP_SIGN_DOUBLE || OP == OP_SIGN_VARGEN) {
+    // out: u, R, (R'), c
+    uint32_t sk[8], nonce[8], u[8];
+    fq Ru, Rv;
+    ldg_scalar(a.in[0] + i * 8, sk);
+    if (OP == OP_SIGN) {  // in: sk, m, nonce
+      ldg_scalar(a.in[2] + i * 8, nonce);
+      sign_core(sk, nonce, ldg_fq(a.in[1] + i * 8), a.combG, u, Ru, Rv, c);
+    } else if (OP == OP_SIGN_DOUBLE) {
+      fq Rpu, Rpv;
+      ldg_scalar(a.in[2] + i * 8, nonce);
+      sign_double_core(sk, nonce, ldg_fq(a.in[1] + i * 8), a.combG, a.combGp, u, Ru, Rv, Rpu, Rpv, c);
+      if (active) stg_point(a.out[2], i, Rpu, Rpv);
+    } else {  // in: sk, gen, m, nonce
+      ldg_scalar(a.in[3] + i * 8, nonce);
+      sign_vargen_core(sk, ldg_point(a.in[1], i, aff), nonce, ldg_fq(a.in[2] + i * 8), u, Ru, Rv, c);
+    }
+    if (active) {
+      stg8(a.out[0] + i * 8, u);
+      stg_point(a.out[1], i, Ru, Rv);
+      if (a.out[3]) stg8(a.out[3] + i * 8, c);
+    }
+    return;
+  }
+
+  if (OP == OP_KEYGEN || OP == OP_KEYGEN_DOUBLE || OP == OP_KEYGEN_VARGEN) {
+    uint32_t sk[8];
+    fq u, v;
+    ldg_scalar(a.in[0] + i * 8, sk);
+    if (OP == OP_KEYGEN_VARGEN) {
+      ext_to_affine(var_base_mul(ldg_point(a.in[1], i, aff), sk), u, v);
+    } else {
+      ext_to_affine(fixed_base_mul(a.combG, sk), u, v);
+    }
+    if (active) stg_point(a.out[0], i, u, v);
+    if (OP == OP_KEYGEN_DOUBLE) {
+      ext_to_affine(fixed_base_mul(a.combGp, sk), u, v);
+      if (active) stg_point(a.out[1], i, u, v);
+    }
+    return;
+  }
+
+  if (OP == OP_DBG_FQ) {
+    fq x = ldg_fq(a.in[0] + i * 8), y = a.in[1] ? ldg_fq(a.in[1] + i * 8) : fq_zero(), r;
+    switch (a.aux) {
+      case 0: r = fq_mul(x, y); break;
+      case 1: r = fq_add(x, y); break;
+      case 2: r = fq_sub(x, y); break;
+      case 3: r = fq_inv(x); break;
+      case 4: r = fq_sqr(x); break;
+      case 5: r = fq_to_mont(x); break;
+      default: r = fq_from_mont(x); break;
+    }
+    if (active) stg8(a.out[0] + i * 8, r.v);
+    return;
+  }
+  if (OP == OP_DBG_FR_MUL) {
+    fr x, y;
+    ldg_scalar(a.in[0] + i * 8, x.v);
+    ldg_scalar(a.in[1] + i * 8, y.v);
+    fr r = fr_mul(x, y);
+    if (active) stg8(a.out[0] + i * 8, r.v);
+    return;
+  }
+  if (OP == OP_DBG_HADES) {
+    fq s[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) s[k] = ldg_fq(a.in[0] + i * 40 + k * 8);
+    if (a.aux) hades_perm_dense(s); else hades_perm(s);
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < 5; k++) stg8(a.out[0] + i * 40 + k * 8, s[k].v);
+    }
+    return;
+  }
+  if (OP == OP_DBG_SMUL) {  // in: points (base 2 only), k
+    uint32_t k[8];
+    fq u, v;
+    ldg_scalar(a.in[1] + i * 8, k);
+    if (a.aux == 2) ext_to_affine(var_base_mul(ldg_point(a.in[0], i, aff), k), u, v);
+    else ext_to_affine(fixed_base_mul(a.aux == 0 ? a.combG : a.combGp, k), u, v);
+    if (active) stg_point(a.out[0], i, u, v);
+    return;
+  }
+}
+
+__global__ void __launch_bounds__(TPB) k_comb_build(uint32_t* table, int which) {
+  int t = blockIdx.x * TPB + threadIdx.x;
+  if (t >= COMB_WINDOWS * COMB_ENTRIES) return;
+  const fq gu = {SB200_G_U_INIT}, gv = {SB200_G_V_INIT}, hu = {SB200_GP_U_INIT}, hv = {SB200_GP_V_INIT};
+  comb_build_entry(which ? hu : gu, which ? hv : gv, t / COMB_ENTRIES, t % COMB_ENTRIES, table + (size_t)t * 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct DevCtx {
+  int dev = 0;
+  cudaStream_t stream[2] = {nullptr, nullptr};
+  uint32_t* combG = nullptr;
+  uint32_t* combGp = nullptr;
+  uint8_t* arena[2] = {nullptr, nullptr};
+  size_t arena_cap[2] = {0, 0};
+};
+
+struct Desc {
+  Op op;
+  uint32_t flags;
+  int aux = 0;
+  int nin = 0, nout = 0;
+  const uint32_t* in[MAX_IN] = {};
+  int in_words[MAX_IN] = {};
+  uint32_t* out[MAX_OUT] = {};
+  int out_words[MAX_OUT] = {};
+  uint32_t* bitmap = nullptr;
+};
+
+}  // namespace
+
+struct sb200_ctx {
+  std::vector<DevCtx> devs;
+  std::mutex mu;
+  std::string err;
+  cudaStream_t user_stream = nullptr;
+  std::atomic<uint64_t> launches{0};
+};
+
+namespace {
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e);                          \
+      return SB200_ERR_CUDA;                                                                  \
+    }                                                                                         \
+  } while (0)
+
+int launch(sb200_ctx* ctx, Op op, const KArgs& a, cudaStream_t st) {
+  if (a.n <= 0) return SB200_OK;
+  unsigned grid = (unsigned)((a.n + TPB - 1) / TPB);
+  switch (op) {
+#define CASE(O) case O: k_run<O><<<grid, TPB, 0, st>>>(a); break;
+    CASE(OP_VERIFY) CASE(OP_VERIFY_DOUBLE) CASE(OP_VERIFY_VARGEN) CASE(OP_SIGN) CASE(OP_SIGN_DOUBLE) CASE(OP_SIGN_VARGEN)
+    CASE(OP_KEYGEN) CASE(OP_KEYGEN_DOUBLE) CASE(OP_KEYGEN_VARGEN) CASE(OP_DBG_FQ) CASE(OP_DBG_FR_MUL) CASE(OP_DBG_HADES)
+    CASE(OP_DBG_SMUL)
+#undef CASE
+  }
+  ctx->launches.fetch_add(1, std::memory_order_relaxed);
+  CU(cudaGetLastError());
+  return SB200_OK;
+}
+
+int run(sb200_ctx* ctx, int64_t n, const Desc& d) {
+  if (!ctx || n < 0) return SB200_ERR_ARG;
+  if (d.flags & ~(SB200_POINTS_AFFINE | SB200_DEVICE_PTRS)) return SB200_ERR_ARG;
+  for (int k = 0; k < d.nin; k++)
+    if (d.in_words[k] && (!d.in[k] || ((uintptr_t)d.in[k] & 15))) return SB200_ERR_ARG;
+  for (int k = 0; k < d.nout; k++)
+    if (d.out[k] && ((uintptr_t)d.out[k] & 15)) return SB200_ERR_ARG;
+  if (n == 0) return SB200_OK;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+
+  if (d.flags & SB200_DEVICE_PTRS) {
+    if (ctx->devs.size() != 1) return SB200_ERR_ARG;
+    DevCtx& dc = ctx->devs[0];
+    CU(cudaSetDevice(dc.dev));
+    KArgs a{};
+    a.n = n; a.flags = d.flags; a.aux = d.aux; a.combG = dc.combG; a.combGp = dc.combGp; a.bitmap = d.bitmap;
+    for (int k = 0; k < d.nin; k++) a.in[k] = d.in[k];
+    for (int k = 0; k < d.nout; k++) a.out[k] = d.out[k];
+    return launch(ctx, d.op, a, ctx->user_stream);
+  }
+
+  // bytes per tuple on the device arena (every array padded to 16 B; bitmap = 4 B per 32 tuples)
+  size_t per_tuple = 0;
+  for (int k = 0; k < d.nin; k++) per_tuple += (size_t)d.in_words[k] * 4;
+  for (int k = 0; k < d.nout; k++) per_tuple += d.out[k] ? (size_t)d.out_words[k] * 4 : 0;
+
+  const int ndev = (int)ctx->devs.size();
+  int64_t per_dev = ((n + ndev - 1) / ndev + 31) & ~(int64_t)31;
+  for (int di = 0; di < ndev; di++) {
+    DevCtx& dc = ctx->devs[di];
+    int64_t lo = std::min<int64_t>(n, di * per_dev), hi = std::min<int64_t>(n, lo + per_dev);
+    if (lo >= hi) continue;
+    CU(cudaSetDevice(dc.dev));
+    int slot = 0;
+    for (int64_t c0 = lo; c0 < hi; c0 += CHUNK, slot ^= 1) {
+      int64_t cn = std::min<int64_t>(CHUNK, hi - c0);
+      size_t need = (size_t)cn * per_tuple + (size_t)((cn + 31) / 32) * 4 + 64 * (MAX_IN + MAX_OUT + 1);
+      if (dc.arena_cap[slot] < need) {
+        CU(cudaStreamSynchronize(dc.stream[slot]));
+        if (dc.arena[slot]) CU(cudaFree(dc.arena[slot]));
+        dc.arena[slot] = nullptr; dc.arena_cap[slot] = 0;
+        size_t cap = std::max(need, (size_t)std::min<int64_t>(CHUNK, per_dev) * per_tuple + (1 << 20));
+        if (cudaMalloc(&dc.arena[slot], cap) != cudaSuccess) { ctx->err = "cudaMalloc arena"; return SB200_ERR_NOMEM; }
+        dc.arena_cap[slot] = cap;
+      }
+      cudaStream_t st = dc.stream[slot];
+      uint8_t* p = dc.arena[slot];
+      auto carve = [&](size_t bytes) { uint8_t* r = p; p += (bytes + 63) & ~(size_t)63; return r; };
+      KArgs a{};
+      a.n = cn; a.flags = d.flags; a.aux = d.aux; a.combG = dc.combG; a.combGp = dc.combGp;
+      for (int k = 0; k < d.nin; k++) {
+        if (!d.in_words[k]) continue;
+        size_t bytes = (size_t)cn * d.in_words[k] * 4;
+        uint32_t* dp = (uint32_t*)carve(bytes);
+        CU(cudaMemcpyAsync(dp, d.in[k] + (size_t)c0 * d.in_words[k], bytes, cudaMemcpyHostToDevice, st));
+        a.in[k] = dp;
+      }
+      uint32_t* dout[MAX_OUT] = {};
+      for (int k = 0; k < d.nout; k++)
+        if (d.out[k]) a.out[k] = dout[k] = (uint32_t*)carve((size_t)cn * d.out_words[k] * 4);
+      uint32_t* dbm = nullptr;
+      if (d.bitmap) a.bitmap = dbm = (uint32_t*)carve((size_t)((cn + 31) / 32) * 4);
+      int rc = launch(ctx, d.op, a, st);
+      if (rc) return rc;
+      for (int k = 0; k < d.nout; k++)
+        if (d.out[k])
+          CU(cudaMemcpyAsync(d.out[k] + (size_t)c0 * d.out_words[k], dout[k], (size_t)cn * d.out_words[k] * 4,
+                             cudaMemcpyDeviceToHost, st));
+      if (d.bitmap)
+        CU(cudaMemcpyAsync(d.bitmap + c0 / 32, dbm, (size_t)((cn + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  for (auto& dc : ctx->devs) {
+    CU(cudaSetDevice(dc.dev));
+    CU(cudaStreamSynchronize(dc.stream[0]));
+    CU(cudaStreamSynchronize(dc.stream[1]));
+  }
+  return SB200_OK;
+}
+
+int pt_words(uint32_t flags) { return (flags & SB200_POINTS_AFFINE) ? 16 : 24; }
+
+}  // namespace
+
+extern "C" {
+
+int sb200_init(const int* devices, int n_devices, sb200_ctx** out) {
+  if (!out || n_devices < 0 || (n_devices > 0 && !devices)) return SB200_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return SB200_ERR_NODEV;
+  int dflt = 0;
+  if (n_devices == 0) { devices = &dflt; n_devices = 1; }
+  sb200_ctx* ctx = new sb200_ctx();
+  auto fail = [&](int code) { sb200_destroy(ctx); return code; };
+  for (int i = 0; i < n_devices; i++) {
+    if (devices[i] < 0 || devices[i] >= count) return fail(SB200_ERR_ARG);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, devices[i]) != cudaSuccess || prop.major < 10) return fail(SB200_ERR_NODEV);
+    DevCtx dc;
+    dc.dev = devices[i];
+    if (cudaSetDevice(dc.dev) != cudaSuccess) return fail(SB200_ERR_CUDA);
+    for (int s = 0; s < 2; s++)
+      if (cudaStreamCreateWithFlags(&dc.stream[s], cudaStreamNonBlocking) != cudaSuccess) return fail(SB200_ERR_CUDA);
+    size_t tb = (size_t)COMB_WINDOWS * COMB_ENTRIES * 24 * 4;
+    if (cudaMalloc(&dc.combG, tb) != cudaSuccess || cudaMalloc(&dc.combGp, tb) != cudaSuccess) return fail(SB200_ERR_NOMEM);
+    ctx->devs.push_back(dc);
+    int grid = (COMB_WINDOWS * COMB_ENTRIES + TPB - 1) / TPB;
+    k_comb_build<<<grid, TPB, 0, dc.stream[0]>>>(dc.combG, 0);
+    k_comb_build<<<grid, TPB, 0, dc.stream[0]>>>(dc.combGp, 1);
+    ctx->launches += 2;
+    if (cudaStreamSynchronize(dc.stream[0]) != cudaSuccess) return fail(SB200_ERR_CUDA);
+  }
+  *out = ctx;
+  return SB200_OK;
+}
+
+void sb200_destroy(sb200_ctx* ctx) {
+  if (!ctx) return;
+  for (auto& dc : ctx->devs) {
+    cudaSetDevice(dc.dev);
+    for (int s = 0; s < 2; s++) {
+      if (dc.stream[s]) { cudaStreamSynchronize(dc.stream[s]); cudaStreamDestroy(dc.stream[s]); }
+      if (dc.arena[s]) cudaFree(dc.arena[s]);
+    }
+    if (dc.combG) cudaFree(dc.combG);
+    if (dc.combGp) cudaFree(dc.combGp);
+  }
+  delete ctx;
+}
+
+const char* sb200_strerror(int code) {
+  switch (code) {
+    case SB200_OK: return "ok";
+    case SB200_ERR_ARG: return "invalid argument";
+    case SB200_ERR_CUDA: return "CUDA error";
+    case SB200_ERR_NODEV: return "no usable sm_100 CUDA device";
+    case SB200_ERR_NOMEM: return "out of device memory";
+    default: return "unknown error";
+  }
+}
+const char* sb200_last_error(const sb200_ctx* ctx) { return ctx ? ctx->err.c_str() : ""; }
+int sb200_device_count(const sb200_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+int sb200_set_stream(sb200_ctx* ctx, void* s) {
+  if (!ctx) return SB200_ERR_ARG;
+  ctx->user_stream = (cudaStream_t)s;
+  return SB200_OK;
+}
+uint64_t sb200_launch_count(const sb200_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+int sb200_host_alloc(size_t bytes, void** out) {
+  if (!out) return SB200_ERR_ARG;
+  return cudaHostAlloc(out, bytes, cudaHostAllocPortable) == cudaSuccess ? SB200_OK : SB200_ERR_NOMEM;
+}
+void sb200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+#define IN(k, ptr, words) d.in[k] = (ptr); d.in_words[k] = (words)
+#define OUT(k, ptr, words) d.out[k] = (ptr); d.out_words[k] = (words)
+
+int sb200_verify(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* pk, const uint32_t* sig_u, const uint32_t* sig_R,
+                 const uint32_t* msg, uint32_t* verdicts, uint32_t* c_out) {
+  if (!verdicts) return SB200_ERR_ARG;
+  Desc d; d.op = OP_VERIFY; d.flags = flags; d.nin = 4; d.nout = 1; d.bitmap = verdicts;
+  IN(0, pk, pt_words(flags)); IN(1, sig_u, 8); IN(2, sig_R, pt_words(flags)); IN(3, msg, 8); OUT(0, c_out, 8);
+  return run(ctx, n, d);
+}
+int sb200_verify_double(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* pk, const uint32_t* pkp, const uint32_t* sig_u,
+                        const uint32_t* sig_R, const uint32_t* sig_Rp, const uint32_t* msg, uint32_t* verdicts, uint32_t* c_out) {
+  if (!verdicts) return SB200_ERR_ARG;
+  Desc d; d.op = OP_VERIFY_DOUBLE; d.flags = flags; d.nin = 6; d.nout = 1; d.bitmap = verdicts;
+  int pw = pt_words(flags);
+  IN(0, pk, pw); IN(1, pkp, pw); IN(2, sig_u, 8); IN(3, sig_R, pw); IN(4, sig_Rp, pw); IN(5, msg, 8); OUT(0, c_out, 8);
+  return run(ctx, n, d);
+}
+int sb200_verify_vargen(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* pk, const uint32_t* gen, const uint32_t* sig_u,
+                        const uint32_t* sig_R, const uint32_t* msg, uint32_t* verdicts, uint32_t* c_out) {
+  if (!verdicts) return SB200_ERR_ARG;
+  Desc d; d.op = OP_VERIFY_VARGEN; d.flags = flags; d.nin = 5; d.nout = 1; d.bitmap = verdicts;
+  int pw = pt_words(flags);
+  IN(0, pk, pw); IN(1, gen, pw); IN(2, sig_u, 8); IN(3, sig_R, pw); IN(4, msg, 8); OUT(0, c_out, 8);
+  return run(ctx, n, d);
+}
+int sb200_sign(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* sk, const uint32_t* msg, const uint32_t* nonce,
+               uint32_t* u_out, uint32_t* R_out, uint32_t* c_out) {
+  if (!u_out || !R_out) return SB200_ERR_ARG;
+  Desc d; d.op = OP_SIGN; d.flags = flags; d.nin = 3; d.nout = 4;
+  IN(0, sk, 8); IN(1, msg, 8); IN(2, nonce, 8); OUT(0, u_out, 8); OUT(1, R_out, 16); OUT(3, c_out, 8);
+  return run(ctx, n, d);
+}
+int sb200_sign_double(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* sk, const uint32_t* msg, const uint32_t* nonce,
+                      uint32_t* u_out, uint32_t* R_out, uint32_t* Rp_out, uint32_t* c_out) {
+  if (!u_out || !R_out || !Rp_out) return SB200_ERR_ARG;
+  Desc d; d.op = OP_SIGN_DOUBLE; d.flags = flags; d.nin = 3; d.nout = 4;
+  IN(0, sk, 8); IN(1, msg, 8); IN(2, nonce, 8); OUT(0, u_out, 8); OUT(1, R_out, 16); OUT(2, Rp_out, 16); OUT(3, c_out, 8);
+  return run(ctx, n, d);
+}
+int sb200_sign_vargen(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* sk, const uint32_t* gen, const uint32_t* msg,
+                      const uint32_t* nonce, uint32_t* u_out, uint32_t* R_out, uint32_t* c_out) {
+  if (!u_out || !R_out) return SB200_ERR_ARG;
+  Desc d; d.op = OP_SIGN_VARGEN; d.flags = flags; d.nin = 4; d.nout = 4;
+  IN(0, sk, 8); IN(1, gen, pt_words(flags)); IN(2, msg, 8); IN(3, nonce, 8); OUT(0, u_out, 8); OUT(1, R_out, 16); OUT(3, c_out, 8);
+  return run(ctx, n, d);
+}
+int sb200_keygen(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* sk, uint32_t* pk_out) {
+  if (!pk_out) return SB200_ERR_ARG;
+  Desc d; d.op = OP_KEYGEN; d.flags = flags; d.nin = 1; d.nout = 1;
+  IN(0, sk, 8); OUT(0, pk_out, 16);
+  return run(ctx, n, d);
+}
+int sb200_keygen_double(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* sk, uint32_t* pk_out, uint32_t* pkp_out) {
+  if (!pk_out || !pkp_out) return SB200_ERR_ARG;
+  Desc d; d.op = OP_KEYGEN_DOUBLE; d.flags = flags; d.nin = 1; d.nout = 2;
+  IN(0, sk, 8); OUT(0, pk_out, 16); OUT(1, pkp_out, 16);
+  return run(ctx, n, d);
+}
+int sb200_keygen_vargen(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* sk, const uint32_t* gen, uint32_t* pk_out) {
+  if (!pk_out) return SB200_ERR_ARG;
+  Desc d; d.op = OP_KEYGEN_VARGEN; d.flags = flags; d.nin = 2; d.nout = 1;
+  IN(0, sk, 8); IN(1, gen, pt_words(flags)); OUT(0, pk_out, 16);
+  return run(ctx, n, d);
+}
+int sb200_dbg_fq(sb200_ctx* ctx, int64_t n, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  if (!out || op < 0 || op > 6) return SB200_ERR_ARG;
+  Desc d; d.op = OP_DBG_FQ; d.flags = 0; d.aux = op; d.nin = 2; d.nout = 1;
+  IN(0, a, 8); IN(1, b, b ? 8 : 0); OUT(0, out, 8);
+  return run(ctx, n, d);
+}
+int sb200_dbg_fr_mul(sb200_ctx* ctx, int64_t n, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  if (!out) return SB200_ERR_ARG;
+  Desc d; d.op = OP_DBG_FR_MUL; d.flags = 0; d.nin = 2; d.nout = 1;
+  IN(0, a, 8); IN(1, b, 8); OUT(0, out, 8);
+  return run(ctx, n, d);
+}
+int sb200_dbg_hades(sb200_ctx* ctx, int64_t n, int dense, uint32_t* states) {
+  if (!states) return SB200_ERR_ARG;
+  Desc d; d.op = OP_DBG_HADES; d.flags = 0; d.aux = dense; d.nin = 1; d.nout = 1;
+  IN(0, states, 40); OUT(0, states, 40);
+  return run(ctx, n, d);
+}
+int sb200_dbg_scalar_mul(sb200_ctx* ctx, int64_t n, uint32_t flags, int base, const uint32_t* points, const uint32_t* k, uint32_t* out) {
+  if (!out || base < 0 || base > 2 || (base == 2 && !points)) return SB200_ERR_ARG;
+  Desc d; d.op = OP_DBG_SMUL; d.flags = flags; d.aux = base; d.nin = 2; d.nout = 1;
+  IN(0, points, base == 2 ? pt_words(flags) : 0); IN(1, k, 8); OUT(0, out, 16);
+  return run(ctx, n, d);
+}
+
+}  // extern "C"

@@ -1,0 +1,60 @@
+// Host-side build of the arithmetic headers (the emulated carry-chain blocks), exported with C
+// linkage so pytest can drive it through ctypes and compare with the big-int oracle on the CPU.
+// Test scaffolding: never linked into libschnorr_b200.so.
+#include <cstring>
+#include <vector>
+#include "../schnorr_b200/csrc/core.cuh"
+using namespace sb200;
+
+static fq L(const uint32_t* p) { fq r; memcpy(r.v, p, 32); return r; }
+static void S(uint32_t* p, const fq& a) { memcpy(p, a.v, 32); }
+
+extern "C" {
+void h_fq_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { S(r, fq_mul(L(a), L(b))); }
+void h_fq_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { S(r, fq_add(L(a), L(b))); }
+void h_fq_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { S(r, fq_sub(L(a), L(b))); }
+void h_fq_inv(const uint32_t* a, uint32_t* r) { S(r, fq_inv(L(a))); }
+void h_fr_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) {
+  fr x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); fr z = fr_mul(x, y); memcpy(r, z.v, 32);
+}
+void h_hades(uint32_t* st, int dense) {
+  fq s[5]; for (int i = 0; i < 5; i++) s[i] = L(st + 8 * i);
+  if (dense) hades_perm_dense(s); else hades_perm(s);
+  for (int i = 0; i < 5; i++) S(st + 8 * i, s[i]);
+}
+// comb table for base (u, v): 32*129*24 limbs
+void h_comb_build(const uint32_t* bu, const uint32_t* bv, uint32_t* table) {
+  for (int j = 0; j < COMB_WINDOWS; j++)
+    for (int e = 0; e < COMB_ENTRIES; e++) comb_build_entry(L(bu), L(bv), j, e, table + (size_t)(j * COMB_ENTRIES + e) * 24);
+}
+static point_in P(const uint32_t* p, int affine) {
+  point_in r; r.U = L(p); r.V = L(p + 8); r.affine = affine != 0; r.Z = affine ? fq_one() : L(p + 16); return r;
+}
+int h_verify(const uint32_t* pk, const uint32_t* u, const uint32_t* R, const uint32_t* m, int affine, const uint32_t* combG, uint32_t* c) {
+  return verify_core(P(pk, affine), u, P(R, affine), L(m), combG, c);
+}
+int h_verify_vargen(const uint32_t* pk, const uint32_t* gen, const uint32_t* u, const uint32_t* R, const uint32_t* m, int affine, uint32_t* c) {
+  return verify_vargen_core(P(pk, affine), P(gen, affine), u, P(R, affine), L(m), c);
+}
+int h_verify_double(const uint32_t* pk, const uint32_t* pkp, const uint32_t* u, const uint32_t* R, const uint32_t* Rp, const uint32_t* m,
+                    int affine, const uint32_t* combG, const uint32_t* combGp, uint32_t* c) {
+  return verify_double_core(P(pk, affine), P(pkp, affine), u, P(R, affine), P(Rp, affine), L(m), combG, combGp, c);
+}
+void h_sign(const uint32_t* sk, const uint32_t* nonce, const uint32_t* m, const uint32_t* combG, uint32_t* u, uint32_t* Ruv, uint32_t* c) {
+  fq a, b; sign_core(sk, nonce, L(m), combG, u, a, b, c); S(Ruv, a); S(Ruv + 8, b);
+}
+void h_sign_double(const uint32_t* sk, const uint32_t* nonce, const uint32_t* m, const uint32_t* combG, const uint32_t* combGp,
+                   uint32_t* u, uint32_t* Ruv, uint32_t* Rpuv, uint32_t* c) {
+  fq a, b, cc, d; sign_double_core(sk, nonce, L(m), combG, combGp, u, a, b, cc, d, c);
+  S(Ruv, a); S(Ruv + 8, b); S(Rpuv, cc); S(Rpuv + 8, d);
+}
+void h_sign_vargen(const uint32_t* sk, const uint32_t* gen, int affine, const uint32_t* nonce, const uint32_t* m, uint32_t* u, uint32_t* Ruv, uint32_t* c) {
+  fq a, b; sign_vargen_core(sk, P(gen, affine), nonce, L(m), u, a, b, c); S(Ruv, a); S(Ruv + 8, b);
+}
+void h_fixed_mul(const uint32_t* comb, const uint32_t* k, uint32_t* uv) {
+  fq a, b; ext_to_affine(fixed_base_mul(comb, k), a, b); S(uv, a); S(uv + 8, b);
+}
+void h_var_mul(const uint32_t* p, int affine, const uint32_t* k, uint32_t* uv) {
+  fq a, b; ext_to_affine(var_base_mul(P(p, affine), k), a, b); S(uv, a); S(uv + 8, b);
+}
+}

@@ -1,0 +1,49 @@
+"""ctypes driver for build/host_arith.so (CPU build of the CUDA arithmetic headers; test scaffolding)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+Q = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+RADIX = 1 << 256
+
+
+def build():
+    so = os.path.join(ROOT, "build", "host_arith.so")
+    src = os.path.join(ROOT, "tests", "host_arith.cpp")
+    hdrs = [os.path.join(ROOT, "schnorr_b200", "csrc", f) for f in ("fq.cuh", "ed.cuh", "hades.cuh", "core.cuh", "constants_gen.cuh")]
+    newest = max(os.path.getmtime(p) for p in [src] + hdrs)
+    if not os.path.exists(so) or os.path.getmtime(so) < newest:
+        os.makedirs(os.path.dirname(so), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-include",
+                               os.path.join(ROOT, "tests", "host_shim.h"), "-o", so, src])
+    return ctypes.CDLL(so)
+
+
+def limbs(x):
+    return np.frombuffer(int(x).to_bytes(32, "little"), dtype=np.uint32).copy()
+
+
+def to_int(a):
+    return int.from_bytes(np.ascontiguousarray(a, dtype=np.uint32).tobytes(), "little")
+
+
+def mont(x):
+    return limbs(x * RADIX % Q)
+
+
+def unmont(a):
+    return to_int(a) * pow(RADIX, -1, Q) % Q
+
+
+def ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def pt_mont(p, z=None):
+    """affine (u, v) [or projective with z] -> contiguous Montgomery limbs"""
+    if z is None:
+        return np.concatenate([mont(p[0]), mont(p[1])])
+    return np.concatenate([mont(p[0] * z % Q), mont(p[1] * z % Q), mont(z)])
