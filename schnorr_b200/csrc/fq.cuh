@@ -13,7 +13,7 @@
 // limb positions) and Y (pairs aligned to odd positions) so every pair keeps the same two
 // registers for the whole product (no MOV traffic); the per-row right shift by one limb swaps the
 // roles of X and Y.  q = 1 (mod 2^32) makes the Montgomery factor m = -t0 (no multiply) and
-// q[1] = 2^32 - 1 turns two more columns of the reduction into adds: 8 + 6 wide multiplies / row.
+// q[1] = 2^32 - 1 turns two more columns of the reduction into adds: 8 + 7 wide multiplies / row (q[1] is a plain multiply: chains that start with adds do not fuse).
 //
 // Every chain is one asm block on the device and one emulation routine on the host, so the row
 // structure (folds, shifts, carries) is unit-tested on the CPU as well (tests/host_arith_test.cpp);
@@ -42,6 +42,10 @@ struct fq {
 // ------------------------------------------------------------------------------------------
 #if !defined(__CUDA_ARCH__)
 namespace emu {
+// op counters of the host (test) build: the roofline's "work per tuple" is counted, not estimated
+struct counters { unsigned long long wide, fq_mul, fq_sqr, fq_addsub, fr_mul; };
+inline counters& cnt() { static thread_local counters c = {0, 0, 0, 0, 0}; return c; }
+#define SB_COUNT(field, k) (::sb200::emu::cnt().field += (k))
 // acc[0..n) += addend (little-endian limbs) starting at limb `at`; returns carry out of limb n-1
 static inline uint32_t add_at(uint32_t* acc, int n, int at, uint64_t val, uint32_t cin) {
   unsigned __int128 carry = cin;
@@ -55,26 +59,33 @@ static inline uint32_t add_at(uint32_t* acc, int n, int at, uint64_t val, uint32
   return (uint32_t)carry;
 }
 }  // namespace emu
+#else
+#define SB_COUNT(field, k) ((void)0)
 #endif
 
-// Block A:  x0 += xf (fold of the limb that fell off the even array), carry goes into the odd chain;
-//           y[0..7] += a * (b1, b3, b5, b7).  No carry out of y[7] (the running value fits 9 limbs).
-SB_HD void blk_fold_mac_odd(uint32_t& x0, uint32_t xf, uint32_t* y, uint32_t a, uint32_t b1, uint32_t b3,
+// Block A:  x0 += xf + (tprev != 0)   (xf = the limb that fell off the even array at the last shift,
+//           tprev = the limb the previous row cancelled: adding m = -tprev to it carries iff tprev != 0);
+//           the carry of that addition enters the odd chain:  y[0..7] += a * (b1, b3, b5, b7).
+//           No carry out of y[7] (the running value fits 9 limbs).
+SB_HD void blk_fold_mac_odd(uint32_t& x0, uint32_t xf, uint32_t tprev, uint32_t* y, uint32_t a, uint32_t b1, uint32_t b3,
                             uint32_t b5, uint32_t b7) {
 #if defined(__CUDA_ARCH__)
-  asm("add.cc.u32 %0, %0, %9;\n\t"
-      "madc.lo.cc.u32 %1, %10, %11, %1;\n\t"
-      "madc.hi.cc.u32 %2, %10, %11, %2;\n\t"
-      "madc.lo.cc.u32 %3, %10, %12, %3;\n\t"
-      "madc.hi.cc.u32 %4, %10, %12, %4;\n\t"
-      "madc.lo.cc.u32 %5, %10, %13, %5;\n\t"
-      "madc.hi.cc.u32 %6, %10, %13, %6;\n\t"
-      "madc.lo.cc.u32 %7, %10, %14, %7;\n\t"
-      "madc.hi.u32 %8, %10, %14, %8;"
+  asm("{\n\t.reg .u32 t;\n\t"
+      "add.cc.u32 t, %10, 0xffffffff;\n\t"
+      "addc.cc.u32 %0, %0, %9;\n\t"
+      "madc.lo.cc.u32 %1, %11, %12, %1;\n\t"
+      "madc.hi.cc.u32 %2, %11, %12, %2;\n\t"
+      "madc.lo.cc.u32 %3, %11, %13, %3;\n\t"
+      "madc.hi.cc.u32 %4, %11, %13, %4;\n\t"
+      "madc.lo.cc.u32 %5, %11, %14, %5;\n\t"
+      "madc.hi.cc.u32 %6, %11, %14, %6;\n\t"
+      "madc.lo.cc.u32 %7, %11, %15, %7;\n\t"
+      "madc.hi.u32 %8, %11, %15, %8;\n\t}"
       : "+r"(x0), "+r"(y[0]), "+r"(y[1]), "+r"(y[2]), "+r"(y[3]), "+r"(y[4]), "+r"(y[5]), "+r"(y[6]), "+r"(y[7])
-      : "r"(xf), "r"(a), "r"(b1), "r"(b3), "r"(b5), "r"(b7));
+      : "r"(xf), "r"(tprev), "r"(a), "r"(b1), "r"(b3), "r"(b5), "r"(b7));
 #else
-  uint64_t t = (uint64_t)x0 + xf;
+  SB_COUNT(wide, 4);
+  uint64_t t = (uint64_t)x0 + xf + (tprev != 0 ? 1u : 0u);
   x0 = (uint32_t)t;
   uint32_t c = (uint32_t)(t >> 32);
   c = emu::add_at(y, 8, 0, (uint64_t)a * b1, c);
@@ -101,6 +112,7 @@ SB_HD void blk_mac_even(uint32_t* x, uint32_t& ytop, uint32_t a, uint32_t b0, ui
       : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]), "+r"(ytop)
       : "r"(a), "r"(b0), "r"(b2), "r"(b4), "r"(b6));
 #else
+  SB_COUNT(wide, 4);
   uint32_t c = emu::add_at(x, 8, 0, (uint64_t)a * b0, 0);
   c += emu::add_at(x, 8, 2, (uint64_t)a * b2, 0);
   c += emu::add_at(x, 8, 4, (uint64_t)a * b4, 0);
@@ -123,6 +135,7 @@ SB_HD void blk_mac_odd(uint32_t* y, uint32_t a, uint32_t b1, uint32_t b3, uint32
       : "+r"(y[0]), "+r"(y[1]), "+r"(y[2]), "+r"(y[3]), "+r"(y[4]), "+r"(y[5]), "+r"(y[6]), "+r"(y[7])
       : "r"(a), "r"(b1), "r"(b3), "r"(b5), "r"(b7));
 #else
+  SB_COUNT(wide, 4);
   uint32_t c = emu::add_at(y, 8, 0, (uint64_t)a * b1, 0);
   c += emu::add_at(y, 8, 2, (uint64_t)a * b3, 0);
   c += emu::add_at(y, 8, 4, (uint64_t)a * b5, 0);
@@ -131,50 +144,26 @@ SB_HD void blk_mac_odd(uint32_t* y, uint32_t a, uint32_t b1, uint32_t b3, uint32
 #endif
 }
 
-// Fq-specific reduction, even half:  x += m * (1, q2, q4, q6) with m = -x0  =>  x0 becomes 0 and the
-// carry into x1 is (x0 != 0).  Carry out of x[7] goes to ytop.
+// Fq-specific reduction, even half.  q0 = 1 and m = -x0, so x0 + m*q0 = 0 with carry (x0 != 0): that limb
+// pair is not touched here at all (the carry is injected by the next row's fold); the chain starts fresh at
+// limb 2:  x[2..7] += m * (q2, q4, q6), carry out of x[7] goes to ytop.
 SB_HD void blk_red_even_q(uint32_t* x, uint32_t& ytop, uint32_t m, uint32_t q2, uint32_t q4, uint32_t q6) {
 #if defined(__CUDA_ARCH__)
-  asm("add.cc.u32 %0, %0, %9;\n\t"
-      "addc.cc.u32 %1, %1, 0;\n\t"
-      "madc.lo.cc.u32 %2, %9, %10, %2;\n\t"
-      "madc.hi.cc.u32 %3, %9, %10, %3;\n\t"
-      "madc.lo.cc.u32 %4, %9, %11, %4;\n\t"
-      "madc.hi.cc.u32 %5, %9, %11, %5;\n\t"
-      "madc.lo.cc.u32 %6, %9, %12, %6;\n\t"
-      "madc.hi.cc.u32 %7, %9, %12, %7;\n\t"
-      "addc.u32 %8, %8, 0;"
-      : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]), "+r"(ytop)
+  asm("mad.lo.cc.u32 %0, %7, %8, %0;\n\t"
+      "madc.hi.cc.u32 %1, %7, %8, %1;\n\t"
+      "madc.lo.cc.u32 %2, %7, %9, %2;\n\t"
+      "madc.hi.cc.u32 %3, %7, %9, %3;\n\t"
+      "madc.lo.cc.u32 %4, %7, %10, %4;\n\t"
+      "madc.hi.cc.u32 %5, %7, %10, %5;\n\t"
+      "addc.u32 %6, %6, 0;"
+      : "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]), "+r"(ytop)
       : "r"(m), "r"(q2), "r"(q4), "r"(q6));
 #else
-  uint32_t c = emu::add_at(x, 8, 0, (uint64_t)m, 0);
-  c += emu::add_at(x, 8, 2, (uint64_t)m * q2, 0);
+  SB_COUNT(wide, 3);
+  uint32_t c = emu::add_at(x, 8, 2, (uint64_t)m * q2, 0);
   c += emu::add_at(x, 8, 4, (uint64_t)m * q4, 0);
   c += emu::add_at(x, 8, 6, (uint64_t)m * q6, 0);
   ytop += c;
-#endif
-}
-
-// Fq-specific reduction, odd half:  y += m * (q1, q3, q5, q7), q1 = 2^32 - 1, so the first product is
-// (lo, hi) = (t0, m - (t0 != 0)) with t0 = -m = the limb being cancelled; passed in precomputed.
-SB_HD void blk_red_odd_q(uint32_t* y, uint32_t m, uint32_t lo1, uint32_t hi1, uint32_t q3, uint32_t q5, uint32_t q7) {
-#if defined(__CUDA_ARCH__)
-  asm("add.cc.u32 %0, %0, %9;\n\t"
-      "addc.cc.u32 %1, %1, %10;\n\t"
-      "madc.lo.cc.u32 %2, %8, %11, %2;\n\t"
-      "madc.hi.cc.u32 %3, %8, %11, %3;\n\t"
-      "madc.lo.cc.u32 %4, %8, %12, %4;\n\t"
-      "madc.hi.cc.u32 %5, %8, %12, %5;\n\t"
-      "madc.lo.cc.u32 %6, %8, %13, %6;\n\t"
-      "madc.hi.u32 %7, %8, %13, %7;"
-      : "+r"(y[0]), "+r"(y[1]), "+r"(y[2]), "+r"(y[3]), "+r"(y[4]), "+r"(y[5]), "+r"(y[6]), "+r"(y[7])
-      : "r"(m), "r"(lo1), "r"(hi1), "r"(q3), "r"(q5), "r"(q7));
-#else
-  uint32_t c = emu::add_at(y, 8, 0, ((uint64_t)hi1 << 32) | lo1, 0);
-  c += emu::add_at(y, 8, 2, (uint64_t)m * q3, 0);
-  c += emu::add_at(y, 8, 4, (uint64_t)m * q5, 0);
-  c += emu::add_at(y, 8, 6, (uint64_t)m * q7, 0);
-  (void)c;
 #endif
 }
 
@@ -204,6 +193,32 @@ SB_HD uint32_t add8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   c = (uint32_t)t;
 #endif
   return c;
+}
+
+// r = a + b + (t != 0) (8 limbs); the sum is known to fit
+SB_HD void add8c(uint32_t* r, const uint32_t* a, const uint32_t* b, uint32_t t) {
+#if defined(__CUDA_ARCH__)
+  asm("{\n\t.reg .u32 t;\n\t"
+      "add.cc.u32 t, %24, 0xffffffff;\n\t"
+      "addc.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;\n\t}"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]),
+        "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(t));
+#else
+  uint64_t c = t != 0 ? 1 : 0;
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)a[i] + b[i];
+    r[i] = (uint32_t)c;
+    c >>= 32;
+  }
+#endif
 }
 
 // r = a - b (8 limbs), returns borrow mask (0 or 0xffffffff)
@@ -251,6 +266,26 @@ struct FrP {
   static constexpr uint32_t ninv = SB200_FR_NINV;
 };
 
+// q's limbs for the multiplier must sit in ordinary registers: with immediate or uniform-register
+// multiplicands ptxas emits IMAD + IMAD.HI pairs instead of one IMAD.WIDE.U32.X per product.
+#if defined(__CUDACC__)
+// One copy of the modulus per lane: the lane-dependent address makes the loaded limbs "divergent" for
+// ptxas' uniformity analysis, so they stay in ordinary registers.  (With immediate, constant-bank or
+// uniform-register multiplicands ptxas emits IMAD + IMAD.HI.U32.X instead of one IMAD.WIDE.U32.X.)
+#define SB_X32(v) v, v, v, v, v, v, v, v, v, v, v, v, v, v, v, v, v, v, v, v, v, v, v, v, v, v, v, v, v, v, v, v
+__device__ uint32_t d_fq_mod_lane[8 * 32] = {SB_X32(0x00000001u), SB_X32(0xffffffffu), SB_X32(0xfffe5bfeu), SB_X32(0x53bda402u),
+                                            SB_X32(0x09a1d805u), SB_X32(0x3339d808u), SB_X32(0x299d7d48u), SB_X32(0x73eda753u)};
+__device__ uint32_t d_fr_mod_lane[8 * 32] = {SB_X32(0xd6f72cb7u), SB_X32(0xd0970e5eu), SB_X32(0xccc81082u), SB_X32(0xa6682093u),
+                                            SB_X32(0x01343b00u), SB_X32(0x06673b01u), SB_X32(0x6533afa9u), SB_X32(0x0e7db4eau)};
+#endif
+#if defined(__CUDA_ARCH__)
+#define SB_FQ_MOD(i) __ldg(&d_fq_mod_lane[(i) * 32 + (threadIdx.x & 31)])
+#define SB_FR_MOD(i) __ldg(&d_fr_mod_lane[(i) * 32 + (threadIdx.x & 31)])
+#else
+#define SB_FQ_MOD(i) FqP::p(i)
+#define SB_FR_MOD(i) FrP::p(i)
+#endif
+
 template <class P>
 SB_HD void cond_sub_p(uint32_t* r) {  // r in [0, 2p) -> [0, p)
   uint32_t t[8];
@@ -278,6 +313,7 @@ SB_HD fq fq_one() {  // Montgomery 1
 }
 
 SB_HD fq fq_add(const fq& a, const fq& b) {
+  SB_COUNT(fq_addsub, 1);
   fq r;
   add8(r.v, a.v, b.v);  // a + b < 2q < 2^256: no carry
   cond_sub_p<FqP>(r.v);
@@ -285,6 +321,7 @@ SB_HD fq fq_add(const fq& a, const fq& b) {
 }
 
 SB_HD fq fq_sub(const fq& a, const fq& b) {
+  SB_COUNT(fq_addsub, 1);
   fq r;
   uint32_t borrow = sub8(r.v, a.v, b.v);
   uint32_t t[8];
@@ -320,21 +357,28 @@ SB_HD fq fq_select(const fq& a, const fq& b, bool take_b) {
 }
 
 // Montgomery product a * b * 2^-256 mod q, inputs and output canonical (< q).
-SB_HD fq fq_mul(const fq& a, const fq& b) {
-  uint32_t X[8], Y[8], xf = 0;
+// 8 rows x (8 + 7) wide products.
+SB_HD fq fq_mul_inl(const fq& a, const fq& b) {
+  SB_COUNT(fq_mul, 1);
+  uint32_t X[8], Y[8], xf = 0, tprev = 0;
 #pragma unroll
   for (int i = 0; i < 8; i++) X[i] = Y[i] = 0;
+  const uint32_t q1 = SB_FQ_MOD(1), q2 = SB_FQ_MOD(2), q3 = SB_FQ_MOD(3), q4 = SB_FQ_MOD(4), q5 = SB_FQ_MOD(5),
+                 q6 = SB_FQ_MOD(6), q7 = SB_FQ_MOD(7);
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     uint32_t ai = a.v[i];
-    blk_fold_mac_odd(X[0], xf, Y, ai, b.v[1], b.v[3], b.v[5], b.v[7]);
+    blk_fold_mac_odd(X[0], xf, tprev, Y, ai, b.v[1], b.v[3], b.v[5], b.v[7]);
     blk_mac_even(X, Y[7], ai, b.v[0], b.v[2], b.v[4], b.v[6]);
-    uint32_t t0 = X[0];
-    uint32_t m = 0u - t0;
-    uint32_t hi1 = m - (t0 != 0 ? 1u : 0u);
-    blk_red_even_q(X, Y[7], m, FqP::p(2), FqP::p(4), FqP::p(6));
-    blk_red_odd_q(Y, m, t0, hi1, FqP::p(3), FqP::p(5), FqP::p(7));
-    // divide by 2^32: the odd array becomes the even one; X[1] is folded in at the next row
+    tprev = X[0];
+    // m = -tprev (-q^-1 = 2^32 - 1 = q1).  Written as a product with the register copy of q1: when ptxas
+    // sees a negation it folds it into the multiplies below and then emits IMAD + IMAD.HI.U32 pairs for
+    // every product with m instead of IMAD.WIDE.U32.X.
+    uint32_t m = tprev * q1;
+    blk_red_even_q(X, Y[7], m, q2, q4, q6);
+    blk_mac_odd(Y, m, q1, q3, q5, q7);
+    // divide by 2^32: the odd array becomes the even one; X[1] (+ the carry of the cancelled limb) is
+    // folded in by the next row
     xf = X[1];
     uint32_t nx[8], ny[8];
 #pragma unroll
@@ -349,15 +393,36 @@ SB_HD fq fq_mul(const fq& a, const fq& b) {
       Y[k] = ny[k];
     }
   }
-  // value = X + xf + (Y << 32)  (< 2q)
+  // value = X + xf + (tprev != 0) + (Y << 32)  (< 2q)
   fq r;
   uint32_t s[8] = {xf, Y[0], Y[1], Y[2], Y[3], Y[4], Y[5], Y[6]};
-  add8(r.v, X, s);
+  add8c(r.v, X, s, tprev);
   cond_sub_p<FqP>(r.v);
   return r;
 }
 
-SB_HD fq fq_sqr(const fq& a) { return fq_mul(a, a); }
+// The kernels call the multiplier out of line: a verification is ~3600 products, and with every one
+// inlined the kernel is 650 KB of SASS and stalls on instruction fetch (ncu: stall_no_instruction was the
+// top stall reason).  Arguments and result travel in registers (no stack traffic).
+#ifndef SB_MUL_NOINLINE
+#define SB_MUL_NOINLINE 1
+#endif
+#if defined(__CUDACC__) && SB_MUL_NOINLINE
+static __device__ __noinline__ fq fq_mul_ool(fq a, fq b) { return fq_mul_inl(a, b); }
+#endif
+SB_HD fq fq_mul(const fq& a, const fq& b) {
+#if defined(__CUDA_ARCH__) && SB_MUL_NOINLINE
+  return fq_mul_ool(a, b);
+#else
+  return fq_mul_inl(a, b);
+#endif
+}
+
+SB_HD fq fq_sqr(const fq& a) {
+  SB_COUNT(fq_sqr, 1);
+  SB_COUNT(fq_mul, -1);
+  return fq_mul(a, a);
+}
 
 SB_HD fq fq_to_mont(const fq& a) {
   const fq r2 = {SB200_FQ_R2_INIT};
@@ -400,17 +465,18 @@ struct fr {
 };
 
 SB_HD fr fr_mont_mul(const fr& a, const fr& b) {
+  SB_COUNT(fr_mul, 1);
   uint32_t X[8], Y[8], xf = 0;
 #pragma unroll
   for (int i = 0; i < 8; i++) X[i] = Y[i] = 0;
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     uint32_t ai = a.v[i];
-    blk_fold_mac_odd(X[0], xf, Y, ai, b.v[1], b.v[3], b.v[5], b.v[7]);
+    blk_fold_mac_odd(X[0], xf, 0u, Y, ai, b.v[1], b.v[3], b.v[5], b.v[7]);
     blk_mac_even(X, Y[7], ai, b.v[0], b.v[2], b.v[4], b.v[6]);
     uint32_t m = X[0] * FrP::ninv;
-    blk_mac_even(X, Y[7], m, FrP::p(0), FrP::p(2), FrP::p(4), FrP::p(6));
-    blk_mac_odd(Y, m, FrP::p(1), FrP::p(3), FrP::p(5), FrP::p(7));
+    blk_mac_even(X, Y[7], m, SB_FR_MOD(0), SB_FR_MOD(2), SB_FR_MOD(4), SB_FR_MOD(6));
+    blk_mac_odd(Y, m, SB_FR_MOD(1), SB_FR_MOD(3), SB_FR_MOD(5), SB_FR_MOD(7));
     xf = X[1];
     uint32_t nx[8], ny[8];
 #pragma unroll

@@ -10,6 +10,8 @@ static fq L(const uint32_t* p) { fq r; memcpy(r.v, p, 32); return r; }
 static void S(uint32_t* p, const fq& a) { memcpy(p, a.v, 32); }
 
 extern "C" {
+void h_counts_reset() { emu::cnt() = {0, 0, 0, 0, 0}; }
+void h_counts_get(unsigned long long* o) { auto& c = emu::cnt(); o[0] = c.wide; o[1] = c.fq_mul; o[2] = c.fq_sqr; o[3] = c.fq_addsub; o[4] = c.fr_mul; }
 void h_fq_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { S(r, fq_mul(L(a), L(b))); }
 void h_fq_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { S(r, fq_add(L(a), L(b))); }
 void h_fq_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { S(r, fq_sub(L(a), L(b))); }

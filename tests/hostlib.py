@@ -47,3 +47,22 @@ def pt_mont(p, z=None):
     if z is None:
         return np.concatenate([mont(p[0]), mont(p[1])])
     return np.concatenate([mont(p[0] * z % Q), mont(p[1] * z % Q), mont(z)])
+
+
+def comb_tables(lib):
+    """(G table, G' table) as built by the host build of comb_build_entry; cached on disk (slow emulation)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import schnorr_oracle as o
+    cache = os.path.join(ROOT, "build", "host_comb_tables.npy")
+    hdr = os.path.join(ROOT, "schnorr_b200", "csrc", "ed.cuh")
+    if os.path.exists(cache) and os.path.getmtime(cache) > os.path.getmtime(hdr):
+        t = np.load(cache)
+        return t[0].copy(), t[1].copy()
+    tabs = []
+    for B in (o.G, o.G_NUMS):
+        t = np.zeros(32 * 129 * 24, np.uint32)
+        lib.h_comb_build(ptr(mont(B[0])), ptr(mont(B[1])), ptr(t))
+        tabs.append(t)
+    np.save(cache, np.stack(tabs))
+    return tabs[0], tabs[1]

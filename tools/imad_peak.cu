@@ -5,17 +5,17 @@
 // Prints one JSON object: per-instruction results/clk/SM (from clock64 inside the kernel) and
 // results/s for the whole GPU (from CUDA events).  Used as the denominator of roofline.frac.
 #include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cuda_runtime.h>
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { \
   fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); return 1; } } while (0)
 
-constexpr int ITERS = 4096;
 constexpr int CHAINS = 8;
 
 template <int MODE>
-__global__ void __launch_bounds__(256) k(uint32_t* out, long long* cycles, uint32_t seed) {
+__global__ void __launch_bounds__(256) k(uint32_t* out, long long* cycles, uint32_t seed, int ITERS) {
   uint32_t a = seed + threadIdx.x, b = seed * 2654435761u + blockIdx.x;
   uint32_t b1 = b ^ 0x55555555u, b2 = b + 77u, b3 = b * 3u;
   uint32_t x[CHAINS];   // 32-bit chains
@@ -85,14 +85,14 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, long long* cycles, uint3
 }
 
 template <int MODE>
-int run(const char* name, double ops_per_iter, int nsm, int ctas_per_sm, uint32_t* out, long long* cyc, bool last) {
+int run(const char* name, double ops_per_iter, int nsm, int ctas_per_sm, uint32_t* out, long long* cyc, bool last, int ITERS) {
   int grid = nsm * ctas_per_sm, block = 256;
-  for (int w = 0; w < 2; w++) k<MODE><<<grid, block>>>(out, cyc, 12345u + w);
+  for (int w = 0; w < 2; w++) k<MODE><<<grid, block>>>(out, cyc, 12345u + w, ITERS);
   CK(cudaDeviceSynchronize());
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0));
   const int REP = 5;
-  for (int r = 0; r < REP; r++) k<MODE><<<grid, block>>>(out, cyc, 999u + r);
+  for (int r = 0; r < REP; r++) k<MODE><<<grid, block>>>(out, cyc, 999u + r, ITERS);
   CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
   float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= REP;
   long long* h = (long long*)malloc(sizeof(long long) * grid);
@@ -105,19 +105,20 @@ int run(const char* name, double ops_per_iter, int nsm, int ctas_per_sm, uint32_
   return 0;
 }
 
-int main() {
+int main(int argc, char** argv) {
+  int ITERS = argc > 1 ? atoi(argv[1]) : (1 << 17);  // ~20-60 ms per launch: long enough for steady clocks
   cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
   int nsm = p.multiProcessorCount, cps = 8;  // 8 CTAs x 256 thr = 64 warps/SM (full occupancy)
   uint32_t* out; long long* cyc;
   CK(cudaMalloc(&out, sizeof(uint32_t) * nsm * cps * 256)); CK(cudaMalloc(&cyc, sizeof(long long) * nsm * cps));
   printf("{\n  \"gpu\": \"%s\", \"sms\": %d, \"clock_khz_max\": %d,\n", p.name, nsm, p.clockRate);
-  if (run<0>("imad_lo", CHAINS, nsm, cps, out, cyc, false)) return 1;
-  if (run<1>("imad_hi", CHAINS, nsm, cps, out, cyc, false)) return 1;
-  if (run<2>("imad_wide", CHAINS, nsm, cps, out, cyc, false)) return 1;
-  if (run<3>("imad_wide_cc", 8, nsm, cps, out, cyc, false)) return 1;   // 8 wide products / iter
-  if (run<4>("iadd64_pair", CHAINS, nsm, cps, out, cyc, false)) return 1;  // 16 adds / iter
-  if (run<5>("mix_wide4_alu8", 4, nsm, cps, out, cyc, false)) return 1;  // counts the 4 wide products
-  if (run<6>("dfma", CHAINS, nsm, cps, out, cyc, true)) return 1;
+  if (run<0>("imad_lo", CHAINS, nsm, cps, out, cyc, false, ITERS)) return 1;
+  if (run<1>("imad_hi", CHAINS, nsm, cps, out, cyc, false, ITERS)) return 1;
+  if (run<2>("imad_wide", CHAINS, nsm, cps, out, cyc, false, ITERS)) return 1;
+  if (run<3>("imad_wide_cc", 8, nsm, cps, out, cyc, false, ITERS)) return 1;   // 8 wide products / iter
+  if (run<4>("iadd64_pair", CHAINS, nsm, cps, out, cyc, false, ITERS)) return 1;  // 16 adds / iter
+  if (run<5>("mix_wide4_alu8", 4, nsm, cps, out, cyc, false, ITERS)) return 1;  // counts the 4 wide products
+  if (run<6>("dfma", CHAINS, nsm, cps, out, cyc, true, ITERS)) return 1;
   printf("}\n");
   return 0;
 }
