@@ -371,10 +371,11 @@ SB_HD fq fq_mul_inl(const fq& a, const fq& b) {
     blk_fold_mac_odd(X[0], xf, tprev, Y, ai, b.v[1], b.v[3], b.v[5], b.v[7]);
     blk_mac_even(X, Y[7], ai, b.v[0], b.v[2], b.v[4], b.v[6]);
     tprev = X[0];
-    // m = -tprev (-q^-1 = 2^32 - 1 = q1).  Written as a product with the register copy of q1: when ptxas
-    // sees a negation it folds it into the multiplies below and then emits IMAD + IMAD.HI.U32 pairs for
-    // every product with m instead of IMAD.WIDE.U32.X.
-    uint32_t m = tprev * q1;
+    // m = -tprev (-q^-1 = 2^32 - 1).  Written as (tprev ^ q1) + 1 with the register copy of q1 = 2^32 - 1,
+    // which ptxas cannot recognise as a negation: when it does, it folds the negation into the multiplies
+    // below and emits IMAD + IMAD.HI.U32 pairs for every product with m instead of IMAD.WIDE.U32.X.
+    // (Two ALU-pipe instructions; a multiply by q1 would cost the saturated FMA-heavy pipe instead.)
+    uint32_t m = (tprev ^ q1) + 1u;
     blk_red_even_q(X, Y[7], m, q2, q4, q6);
     blk_mac_odd(Y, m, q1, q3, q5, q7);
     // divide by 2^32: the odd array becomes the even one; X[1] (+ the carry of the cancelled limb) is

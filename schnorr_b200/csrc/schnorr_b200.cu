@@ -24,6 +24,10 @@ using namespace sb200;
 namespace {
 
 constexpr int TPB = 128;
+#ifndef SB_MIN_CTAS
+#define SB_MIN_CTAS 4
+#endif
+constexpr int MIN_CTAS = SB_MIN_CTAS;  // 4 CTAs x 128 threads per SM => at most 128 registers per thread
 constexpr int MAX_IN = 6, MAX_OUT = 4;
 constexpr int64_t CHUNK = 1 << 18;  // tuples per pipeline stage
 
@@ -74,7 +78,7 @@ __device__ __forceinline__ void stg_point(uint32_t* base, int64_t i, const fq& u
 }
 
 template <int OP>
-__global__ void __launch_bounds__(TPB) k_run(const KArgs a) {
+__global__ void __launch_bounds__(TPB, MIN_CTAS) k_run(const KArgs a) {
   int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
   const bool active = i < a.n;
   if (!active) i = a.n - 1;  // idle lanes redo the last tuple so the warp stays converged

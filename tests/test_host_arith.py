@@ -1,0 +1,101 @@
+"""The CUDA headers compiled for the CPU (carry-chain blocks emulated): every per-tuple routine the kernels
+run, against the oracle.  Catches logic errors without a GPU; the GPU parity tests then only have to
+catch PTX-level ones."""
+import random
+
+import numpy as np
+import pytest
+
+import hostlib as H
+import schnorr_oracle as o
+import vectors as V
+
+Q, R = o.Q, o.R
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return H.build()
+
+
+@pytest.fixture(scope="module")
+def tabs(lib):
+    return H.comb_tables(lib)
+
+
+def test_fq_fr(lib):
+    rnd = random.Random(1)
+    out = np.zeros(8, np.uint32)
+    vals = [0, 1, 2, Q - 1, Q - 2, (1 << 255) % Q, (1 << 32) - 1, 1 << 32, Q >> 1, 1 << 224, (1 << 224) - 1] + \
+           [rnd.randrange(Q) for _ in range(60)]
+    rinv = pow(H.RADIX, -1, Q)
+    for a in vals:
+        for b in vals[:24]:
+            lib.h_fq_mul(H.ptr(H.limbs(a)), H.ptr(H.limbs(b)), H.ptr(out)); assert H.to_int(out) == a * b * rinv % Q
+            lib.h_fq_add(H.ptr(H.limbs(a)), H.ptr(H.limbs(b)), H.ptr(out)); assert H.to_int(out) == (a + b) % Q
+            lib.h_fq_sub(H.ptr(H.limbs(a)), H.ptr(H.limbs(b)), H.ptr(out)); assert H.to_int(out) == (a - b) % Q
+    for a in vals[1:12]:
+        lib.h_fq_inv(H.ptr(H.mont(a)), H.ptr(out)); assert H.unmont(out) == pow(a, -1, Q)
+    rv = [0, 1, R - 1, (1 << 250) - 1] + [rnd.randrange(R) for _ in range(30)]
+    for a in rv:
+        for b in rv[:8]:
+            lib.h_fr_mul(H.ptr(H.limbs(a)), H.ptr(H.limbs(b)), H.ptr(out)); assert H.to_int(out) == a * b % R
+
+
+@pytest.mark.parametrize("dense", [1, 0])
+def test_hades(lib, dense):
+    rnd = random.Random(2)
+    for st in ([0] * 5, [Q - 1] * 5, [rnd.randrange(Q) for _ in range(5)]):
+        buf = np.concatenate([H.mont(x) for x in st])
+        lib.h_hades(H.ptr(buf), dense)
+        assert [H.unmont(buf[8 * i:8 * i + 8]) for i in range(5)] == o.hades_perm(st)
+
+
+def test_scalar_mul(lib, tabs):
+    rnd = random.Random(3)
+    uv = np.zeros(16, np.uint32)
+    for k in [0, 1, 127, 128, 129, 256, R - 1, R, (1 << 252) - 1, rnd.randrange(R)]:
+        lib.h_fixed_mul(H.ptr(tabs[0]), H.ptr(H.limbs(k)), H.ptr(uv))
+        assert (H.unmont(uv[:8]), H.unmont(uv[8:])) == V.mul(o.G, k)
+        lib.h_fixed_mul(H.ptr(tabs[1]), H.ptr(H.limbs(k)), H.ptr(uv))
+        assert (H.unmont(uv[:8]), H.unmont(uv[8:])) == V.mul(o.G_NUMS, k)
+    for P in V.torsion_points()[:4] + [o.G, V.rand_curve_point(rnd)]:
+        for k in [0, 1, 8, R - 1, R + 5, (1 << 252) - 1, rnd.randrange(1 << 252)]:
+            for aff in (1, 0):
+                pin = H.pt_mont(P) if aff else H.pt_mont(P, rnd.randrange(1, Q))
+                lib.h_var_mul(H.ptr(pin), aff, H.ptr(H.limbs(k)), H.ptr(uv))
+                assert (H.unmont(uv[:8]), H.unmont(uv[8:])) == V.mul(P, k)
+
+
+def test_sign_verify_all_variants(lib, tabs):
+    rnd = random.Random(4)
+    c, u, uv, uvp = np.zeros(8, np.uint32), np.zeros(8, np.uint32), np.zeros(16, np.uint32), np.zeros(16, np.uint32)
+    G, Gp = H.ptr(tabs[0]), H.ptr(tabs[1])
+    for _ in range(2):
+        sk, nonce, m = rnd.randrange(R), rnd.randrange(R), rnd.randrange(Q)
+        z1, z2 = rnd.randrange(1, Q), rnd.randrange(1, Q)
+        eu, eR, ec = o.sign(sk, nonce, m, mul=V.mul)
+        lib.h_sign(H.ptr(H.limbs(sk)), H.ptr(H.limbs(nonce)), H.ptr(H.mont(m)), G, H.ptr(u), H.ptr(uv), H.ptr(c))
+        assert (H.to_int(u), (H.unmont(uv[:8]), H.unmont(uv[8:])), H.to_int(c)) == (eu, eR, ec)
+        pk = V.mul(o.G, sk)
+        assert lib.h_verify(H.ptr(H.pt_mont(pk)), H.ptr(H.limbs(eu)), H.ptr(H.pt_mont(eR)), H.ptr(H.mont(m)), 1, G, H.ptr(c)) == 1
+        assert H.to_int(c) == ec
+        assert lib.h_verify(H.ptr(H.pt_mont(pk, z1)), H.ptr(H.limbs(eu)), H.ptr(H.pt_mont(eR, z2)), H.ptr(H.mont(m)), 0, G, H.ptr(c)) == 1
+        assert lib.h_verify(H.ptr(H.pt_mont(pk)), H.ptr(H.limbs((eu + 1) % R)), H.ptr(H.pt_mont(eR)), H.ptr(H.mont(m)), 1, G, H.ptr(c)) == 0
+        assert lib.h_verify(H.ptr(H.pt_mont(pk)), H.ptr(H.limbs(eu + R)), H.ptr(H.pt_mont(eR)), H.ptr(H.mont(m)), 1, G, H.ptr(c)) == 0
+        eu, eR, eRp, ec = o.sign_double(sk, nonce, m, mul=V.mul)
+        lib.h_sign_double(H.ptr(H.limbs(sk)), H.ptr(H.limbs(nonce)), H.ptr(H.mont(m)), G, Gp, H.ptr(u), H.ptr(uv), H.ptr(uvp), H.ptr(c))
+        assert (H.to_int(u), (H.unmont(uvp[:8]), H.unmont(uvp[8:])), H.to_int(c)) == (eu, eRp, ec)
+        pkp = V.mul(o.G_NUMS, sk)
+        args = lambda a, b, aff: (H.ptr(H.pt_mont(a, None if aff else z1)), H.ptr(H.pt_mont(b, None if aff else z2)), H.ptr(H.limbs(eu)),
+                                  H.ptr(H.pt_mont(eR, None if aff else z2)), H.ptr(H.pt_mont(eRp, None if aff else z1)), H.ptr(H.mont(m)), aff, G, Gp, H.ptr(c))
+        assert lib.h_verify_double(*args(pk, pkp, 1)) == 1 and lib.h_verify_double(*args(pk, pkp, 0)) == 1
+        assert lib.h_verify_double(*args(pk, pk, 1)) == 0
+        gen = V.mul(o.G, rnd.randrange(R))
+        eu, eR, ec = o.sign_vargen(sk, gen, nonce, m, mul=V.mul)
+        lib.h_sign_vargen(H.ptr(H.limbs(sk)), H.ptr(H.pt_mont(gen)), 1, H.ptr(H.limbs(nonce)), H.ptr(H.mont(m)), H.ptr(u), H.ptr(uv), H.ptr(c))
+        assert (H.to_int(u), (H.unmont(uv[:8]), H.unmont(uv[8:])), H.to_int(c)) == (eu, eR, ec)
+        pkv = V.mul(gen, sk)
+        assert lib.h_verify_vargen(H.ptr(H.pt_mont(pkv)), H.ptr(H.pt_mont(gen)), H.ptr(H.limbs(eu)), H.ptr(H.pt_mont(eR)), H.ptr(H.mont(m)), 1, H.ptr(c)) == 1
+        assert lib.h_verify_vargen(H.ptr(H.pt_mont(pkv, z1)), H.ptr(H.pt_mont(gen, z2)), H.ptr(H.limbs(eu)), H.ptr(H.pt_mont(eR, z1)), H.ptr(H.mont(m)), 0, H.ptr(c)) == 1
+        assert lib.h_verify_vargen(H.ptr(H.pt_mont(pkv)), H.ptr(H.pt_mont(o.G)), H.ptr(H.limbs(eu)), H.ptr(H.pt_mont(eR)), H.ptr(H.mont(m)), 1, H.ptr(c)) == 0

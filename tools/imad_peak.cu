@@ -9,6 +9,9 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#define SB_MUL_NOINLINE 0
+#include "../schnorr_b200/csrc/fq.cuh"
+
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { \
   fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); return 1; } } while (0)
 
@@ -21,14 +24,16 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, long long* cycles, uint3
   uint32_t x[CHAINS];   // 32-bit chains
   uint64_t v[CHAINS];   // 64-bit chains (aligned register pairs)
   double d[CHAINS];
+  uint32_t w[16];      // 32-bit pairs for the carry-chain mode
 #pragma unroll
   for (int i = 0; i < CHAINS; i++) {
     x[i] = a ^ (i * 0x9e3779b9u);
     v[i] = ((uint64_t)(b + i) << 32) | x[i];
     d[i] = 1.0 + 1e-3 * (double)(x[i] & 1023);
+    w[2 * i] = x[i] * 3u; w[2 * i + 1] = x[i] ^ b;
   }
   long long t0 = clock64();
-#pragma unroll 1
+#pragma unroll (MODE == 7 ? 1 : 8)
   for (int it = 0; it < ITERS; it++) {
     if (MODE == 0) {  // IMAD (mad.lo), multiplicand = running value so ptxas cannot hoist the product
 #pragma unroll
@@ -41,23 +46,24 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, long long* cycles, uint3
       for (int c = 0; c < CHAINS; c++)
         asm volatile("{\n\t.reg .u32 l,h;\n\tmov.b64 {l,h}, %2;\n\tmad.wide.u32 %0, l, %1, %0;\n\t}" : "+l"(v[c]) : "r"(a), "l"(v[(c + 3) % CHAINS]));
     } else if (MODE == 3) {
-      // two independent 4-product carry chains: (mad.lo.cc, madc.hi.cc) x4 -> IMAD.WIDE.U32 + 3x IMAD.WIDE.U32.X
+      // the multiplier's building block: two independent carry chains of 4 products each,
+      // (mad.lo.cc, madc.hi.cc) x4 -> IMAD.WIDE.U32 + 3x IMAD.WIDE.U32.X, accumulating in place.
+      // The multiplier operand is a running value so ptxas cannot hoist a product out of the loop.
 #pragma unroll
       for (int h = 0; h < 2; h++) {
+        uint32_t* y = w + 8 * h;
+        uint32_t mul = w[8 * (1 - h)];
         asm volatile(
-            "{\n\t.reg .u32 l0,h0,l1,h1,l2,h2,l3,h3;\n\t"
-            "mov.b64 {l0,h0}, %0; mov.b64 {l1,h1}, %1; mov.b64 {l2,h2}, %2; mov.b64 {l3,h3}, %3;\n\t"
-            "mad.lo.cc.u32 l0, %4, %5, l0;\n\t"
-            "madc.hi.cc.u32 h0, %4, %5, h0;\n\t"
-            "madc.lo.cc.u32 l1, %4, %6, l1;\n\t"
-            "madc.hi.cc.u32 h1, %4, %6, h1;\n\t"
-            "madc.lo.cc.u32 l2, %4, %7, l2;\n\t"
-            "madc.hi.cc.u32 h2, %4, %7, h2;\n\t"
-            "madc.lo.cc.u32 l3, %4, %8, l3;\n\t"
-            "madc.hi.u32 h3, %4, %8, h3;\n\t"
-            "mov.b64 %0, {l0,h0}; mov.b64 %1, {l1,h1}; mov.b64 %2, {l2,h2}; mov.b64 %3, {l3,h3};\n\t}"
-            : "+l"(v[4 * h]), "+l"(v[4 * h + 1]), "+l"(v[4 * h + 2]), "+l"(v[4 * h + 3])
-            : "r"(a), "r"(b), "r"(b1), "r"(b2), "r"(b3));
+            "mad.lo.cc.u32 %0, %8, %9, %0;\n\t"
+            "madc.hi.cc.u32 %1, %8, %9, %1;\n\t"
+            "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+            "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+            "madc.lo.cc.u32 %4, %8, %11, %4;\n\t"
+            "madc.hi.cc.u32 %5, %8, %11, %5;\n\t"
+            "madc.lo.cc.u32 %6, %8, %12, %6;\n\t"
+            "madc.hi.u32 %7, %8, %12, %7;"
+            : "+r"(y[0]), "+r"(y[1]), "+r"(y[2]), "+r"(y[3]), "+r"(y[4]), "+r"(y[5]), "+r"(y[6]), "+r"(y[7])
+            : "r"(mul), "r"(b), "r"(b1), "r"(b2), "r"(b3));
       }
     } else if (MODE == 4) {  // 64-bit add as add.cc/addc pair (ALU-pipe IADD3 [+ IMAD.X])
 #pragma unroll
@@ -71,6 +77,14 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, long long* cycles, uint3
         asm volatile("add.u32 %0, %0, %1;" : "+r"(x[c]) : "r"(b));
         asm volatile("xor.b32 %0, %0, %1;" : "+r"(x[4 + c]) : "r"(a));
       }
+    } else if (MODE == 7) {  // the library's Fq Montgomery multiplier, inlined: 120 wide products per call
+      sb200::fq fa, fb;
+#pragma unroll
+      for (int c = 0; c < 8; c++) { fa.v[c] = w[c]; fb.v[c] = w[8 + c]; }
+      fa = sb200::fq_mul_inl(fa, fb);
+      fb = sb200::fq_mul_inl(fb, fa);
+#pragma unroll
+      for (int c = 0; c < 8; c++) { w[c] = fa.v[c]; w[8 + c] = fb.v[c]; }
     } else if (MODE == 6) {  // DFMA
 #pragma unroll
       for (int c = 0; c < CHAINS; c++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[c]) : "d"(1.0000001), "d"(1e-9));
@@ -79,7 +93,7 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, long long* cycles, uint3
   long long t1 = clock64();
   uint32_t acc = 0;
 #pragma unroll
-  for (int i = 0; i < CHAINS; i++) acc ^= x[i] ^ (uint32_t)v[i] ^ (uint32_t)(v[i] >> 32) ^ (uint32_t)__double2loint(d[i]);
+  for (int i = 0; i < CHAINS; i++) acc ^= w[2 * i] ^ w[2 * i + 1] ^ x[i] ^ (uint32_t)v[i] ^ (uint32_t)(v[i] >> 32) ^ (uint32_t)__double2loint(d[i]);
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
   if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
@@ -98,10 +112,16 @@ int run(const char* name, double ops_per_iter, int nsm, int ctas_per_sm, uint32_
   long long* h = (long long*)malloc(sizeof(long long) * grid);
   CK(cudaMemcpy(h, cyc, sizeof(long long) * grid, cudaMemcpyDeviceToHost));
   double avg = 0; for (int i = 0; i < grid; i++) avg += (double)h[i]; avg /= grid; free(h);
+  int resident = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k<MODE>, block, 0);
   double total_ops = ops_per_iter * ITERS * (double)block * grid;
   double per_clk_sm = ops_per_iter * ITERS * (double)block * ctas_per_sm / avg;  // thread-level results / clk / SM
-  printf("  \"%s\": {\"per_clk_sm\": %.2f, \"per_s\": %.4e, \"ms\": %.4f, \"eff_mhz\": %.0f}%s\n", name, per_clk_sm,
-         total_ops / (ms * 1e-3), ms, avg / (ms * 1e3), last ? "" : ",");
+  (void)per_clk_sm;
+  // every CTA counts its own cycles; with `resident` CTAs per SM a launch is ceil(cps/resident) waves long
+  double waves = (double)((ctas_per_sm + resident - 1) / resident);
+  double sm_cycles = avg * waves;
+  printf("  \"%s\": {\"per_s\": %.4e, \"per_clk_sm\": %.2f, \"ms\": %.4f, \"sm_mhz_during\": %.0f, \"resident_ctas\": %d}%s\n", name,
+         total_ops / (ms * 1e-3), total_ops / nsm / sm_cycles, ms, sm_cycles / (ms * 1e3), resident, last ? "" : ",");
   return 0;
 }
 
@@ -118,7 +138,8 @@ int main(int argc, char** argv) {
   if (run<3>("imad_wide_cc", 8, nsm, cps, out, cyc, false, ITERS)) return 1;   // 8 wide products / iter
   if (run<4>("iadd64_pair", CHAINS, nsm, cps, out, cyc, false, ITERS)) return 1;  // 16 adds / iter
   if (run<5>("mix_wide4_alu8", 4, nsm, cps, out, cyc, false, ITERS)) return 1;  // counts the 4 wide products
-  if (run<6>("dfma", CHAINS, nsm, cps, out, cyc, true, ITERS)) return 1;
+  if (run<6>("dfma", CHAINS, nsm, cps, out, cyc, false, ITERS)) return 1;
+  if (run<7>("fq_mul_wide_products", 240, nsm, 4, out, cyc, true, ITERS / 16)) return 1;  // 2 muls x 120 products / iter
   printf("}\n");
   return 0;
 }

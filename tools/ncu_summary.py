@@ -1,0 +1,25 @@
+"""Key metrics from an .ncu-rep (raw page) -> text.  usage: python tools/ncu_summary.py X.ncu-rep"""
+import csv, subprocess, sys, io
+rep = sys.argv[1]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units = rows[0], rows[1]
+want = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__grid_size",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "sm__cycles_elapsed.avg.per_second",
+        "sm__cycles_elapsed.avg", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__warps_eligible.avg.per_cycle_active",
+        "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_local_st.sum",
+        "l1tex__t_sector_pipe_lsu_mem_local_op_ld_hit_rate.pct"]
+for r in rows[2:]:
+    d = dict(zip(hdr, r))
+    for k in want:
+        if k in d:
+            print(f"{k:75s} {d[k]:>22s} {units[hdr.index(k)]}")
+    print("-- stall reasons (warps stalled per issue-active cycle) --")
+    st = [(float(d[k]), k.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")) for k in hdr
+          if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio")]
+    for v, k in sorted(st, reverse=True)[:8]:
+        print(f"   {k:30s} {v:8.3f}")
