@@ -12,7 +12,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libschnorr_b200.so")
+LIB_PATH = os.environ.get("SB200_LIB", os.path.join(_HERE, "libschnorr_b200.so"))  # override: kernel-variant experiments
 
 POINTS_PROJECTIVE = 0
 POINTS_AFFINE = 1

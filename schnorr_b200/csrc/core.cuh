@@ -63,7 +63,7 @@ SB_HD bool verify_core(const point_in& PK, const uint32_t* u_in, const point_in&
   vartable_build(tab, point_to_ext(PK));
   recode_offset<4>(c);
   p1p1 cp = ed_mul_var(tab, c, 63);  // c < 2^250: 63 windows
-  recode_offset<8>(u);
+  recode_offset<COMB_BITS>(u);
   cp = ed_comb_add(p1p1_to_ext(cp), combG, u);
   return ok & p1p1_equals(cp, R);
 }
@@ -111,7 +111,7 @@ SB_HD bool verify_double_core(const point_in& PK, const point_in& PKp, const uin
 #pragma unroll
   for (int i = 0; i < 8; i++) u[i] = ok ? u_in[i] : 0u;
   recode_offset<4>(c);
-  recode_offset<8>(u);
+  recode_offset<COMB_BITS>(u);
   pniels tab[9];
   vartable_build(tab, point_to_ext(PK));
   p1p1 cp = ed_mul_var(tab, c, 63);
@@ -149,7 +149,7 @@ SB_HD ext fixed_base_mul(const uint32_t* comb, const uint32_t* k) {
   uint32_t kr[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) kr[i] = k[i];
-  recode_offset<8>(kr);
+  recode_offset<COMB_BITS>(kr);
   return p1p1_to_ext(ed_comb_add(ext_identity(), comb, kr));
 }
 

@@ -11,7 +11,7 @@
 // (/root/reference/tests/keys.rs:52-58), so the schedules here are free to differ:
 //   * variable base  : signed fixed windows (regular recoding, identical control flow in all 32
 //                      lanes -- a wNAF's data-dependent add positions would diverge per lane);
-//   * fixed base G/G': comb of 8-bit signed windows, 32 mixed additions and no doublings.
+//   * fixed base G/G': comb of 16-bit signed windows, 16 mixed additions and no doublings.
 #pragma once
 #include "fq.cuh"
 
@@ -33,6 +33,19 @@ struct aniels {  // affine Niels form (Z = 1): (y+x, y-x, 2d*x*y)
   fq YpX, YmX, T2d;
 };
 
+// INL = true: multiplier bodies inlined (used inside the "fat" out-of-line point operations below);
+// INL = false: the out-of-line multiplier.
+template <bool INL>
+SB_HD fq mulT(const fq& a, const fq& b) {
+  if (INL) return fq_mul_inl(a, b);
+  return fq_mul(a, b);
+}
+template <bool INL>
+SB_HD fq sqrT(const fq& a) {
+  if (INL) return fq_sqr_inl(a);
+  return fq_sqr(a);
+}
+
 SB_HD fq ed_2d() {
   const fq c = {SB200_ED_2D_INIT};
   return c;
@@ -51,28 +64,31 @@ SB_HD ext ext_identity() {
   return r;
 }
 
+template <bool INL = false>
 SB_HD proj p1p1_to_proj(const p1p1& c) {
   proj r;
-  r.X = fq_mul(c.E, c.F);
-  r.Y = fq_mul(c.G, c.H);
-  r.Z = fq_mul(c.F, c.G);
+  r.X = mulT<INL>(c.E, c.F);
+  r.Y = mulT<INL>(c.G, c.H);
+  r.Z = mulT<INL>(c.F, c.G);
   return r;
 }
+template <bool INL = false>
 SB_HD ext p1p1_to_ext(const p1p1& c) {
   ext r;
-  r.X = fq_mul(c.E, c.F);
-  r.Y = fq_mul(c.G, c.H);
-  r.Z = fq_mul(c.F, c.G);
-  r.T = fq_mul(c.E, c.H);
+  r.X = mulT<INL>(c.E, c.F);
+  r.Y = mulT<INL>(c.G, c.H);
+  r.Z = mulT<INL>(c.F, c.G);
+  r.T = mulT<INL>(c.E, c.H);
   return r;
 }
 
 // 2P, 4 squarings (dbl-2008-hwcd with a = -1, signs arranged so H = A + B, F = C - G)
+template <bool INL = false>
 SB_HD p1p1 ed_dbl(const fq& X, const fq& Y, const fq& Z) {
-  fq A = fq_sqr(X);
-  fq B = fq_sqr(Y);
-  fq C = fq_dbl(fq_sqr(Z));
-  fq S = fq_sqr(fq_add(X, Y));
+  fq A = sqrT<INL>(X);
+  fq B = sqrT<INL>(Y);
+  fq C = fq_dbl(sqrT<INL>(Z));
+  fq S = sqrT<INL>(fq_add(X, Y));
   p1p1 r;
   r.H = fq_add(A, B);
   r.G = fq_sub(B, A);
@@ -82,11 +98,12 @@ SB_HD p1p1 ed_dbl(const fq& X, const fq& Y, const fq& Z) {
 }
 
 // P + Q, Q in projective Niels form: 4 multiplications (add-2008-hwcd-3, k = 2d)
+template <bool INL = false>
 SB_HD p1p1 ed_add(const ext& p, const pniels& q) {
-  fq A = fq_mul(fq_sub(p.Y, p.X), q.YmX);
-  fq B = fq_mul(fq_add(p.Y, p.X), q.YpX);
-  fq C = fq_mul(p.T, q.T2d);
-  fq D = fq_dbl(fq_mul(p.Z, q.Z));
+  fq A = mulT<INL>(fq_sub(p.Y, p.X), q.YmX);
+  fq B = mulT<INL>(fq_add(p.Y, p.X), q.YpX);
+  fq C = mulT<INL>(p.T, q.T2d);
+  fq D = fq_dbl(mulT<INL>(p.Z, q.Z));
   p1p1 r;
   r.E = fq_sub(B, A);
   r.F = fq_sub(D, C);
@@ -96,10 +113,11 @@ SB_HD p1p1 ed_add(const ext& p, const pniels& q) {
 }
 
 // P + Q, Q affine Niels: 3 multiplications
+template <bool INL = false>
 SB_HD p1p1 ed_add(const ext& p, const aniels& q) {
-  fq A = fq_mul(fq_sub(p.Y, p.X), q.YmX);
-  fq B = fq_mul(fq_add(p.Y, p.X), q.YpX);
-  fq C = fq_mul(p.T, q.T2d);
+  fq A = mulT<INL>(fq_sub(p.Y, p.X), q.YmX);
+  fq B = mulT<INL>(fq_add(p.Y, p.X), q.YpX);
+  fq C = mulT<INL>(p.T, q.T2d);
   fq D = fq_dbl(p.Z);
   p1p1 r;
   r.E = fq_sub(B, A);
@@ -168,8 +186,8 @@ SB_HD ext affine_to_ext(const fq& u, const fq& v) {
 // ------------------------------------------------------------------------------------------
 template <int W>
 SB_HD void recode_offset(uint32_t* k) {  // k += sum_i 2^(W-1) * 2^(W*i) over all windows that fit in 256 bits
-  static_assert(W == 4 || W == 8, "window widths that tile 32-bit limbs");
-  const uint32_t c = (W == 4) ? 0x88888888u : 0x80808080u;
+  static_assert(W == 4 || W == 8 || W == 16, "window widths that tile 32-bit limbs");
+  const uint32_t c = (W == 4) ? 0x88888888u : (W == 8) ? 0x80808080u : 0x80008000u;
   const uint32_t off[8] = {c, c, c, c, c, c, c, c};
   add8(k, k, off);  // k < 2^252 => no carry out
 }
@@ -197,6 +215,30 @@ SB_HD void vartable_build(pniels* tab, const ext& P) {
   }
 }
 
+// ---- "fat" out-of-line point steps --------------------------------------------------------------
+// One call per point operation with the 7-8 multiplications inlined inside: the completed point travels
+// in registers (32 in, 32 out), so the per-multiplication argument shuffling of the out-of-line
+// multiplier (ptxas emits half of those moves as IMAD.MOV on the saturated FMA-heavy pipe) disappears
+// from the hot loops, while the code stays small enough for the instruction cache.
+#ifndef SB_FAT_OOL
+#define SB_FAT_OOL 0  // measured: 27 KB per fat step thrashes the instruction cache (stall_no_instruction 0.12 -> 1.24); kept for experiments
+#endif
+#if defined(__CUDACC__) && SB_FAT_OOL
+static __device__ __noinline__ p1p1 pt_dbl_ool(p1p1 c) {
+  proj p = p1p1_to_proj<true>(c);
+  return ed_dbl<true>(p.X, p.Y, p.Z);
+}
+#endif
+// c <- 2c   (3M + 4S)
+SB_HD p1p1 pt_dbl(const p1p1& c) {
+#if defined(__CUDA_ARCH__) && SB_FAT_OOL
+  return pt_dbl_ool(c);
+#else
+  proj p = p1p1_to_proj(c);
+  return ed_dbl(p.X, p.Y, p.Z);
+#endif
+}
+
 SB_HD pniels vartable_lookup(const pniels* tab, int d) {
   bool neg = d < 0;
   int idx = neg ? -d : d;
@@ -208,14 +250,10 @@ SB_HD p1p1 ed_mul_var(const pniels* tab, const uint32_t* k_rec, int nwin) {
   p1p1 c = ed_add(ext_identity(), vartable_lookup(tab, recode_digit<4>(k_rec, nwin - 1)));
 #pragma unroll 1
   for (int i = nwin - 2; i >= 0; i--) {
-    proj p = p1p1_to_proj(c);
-    c = ed_dbl(p.X, p.Y, p.Z);
-    p = p1p1_to_proj(c);
-    c = ed_dbl(p.X, p.Y, p.Z);
-    p = p1p1_to_proj(c);
-    c = ed_dbl(p.X, p.Y, p.Z);
-    p = p1p1_to_proj(c);
-    c = ed_dbl(p.X, p.Y, p.Z);
+    c = pt_dbl(c);
+    c = pt_dbl(c);
+    c = pt_dbl(c);
+    c = pt_dbl(c);
     ext e = p1p1_to_ext(c);
     c = ed_add(e, vartable_lookup(tab, recode_digit<4>(k_rec, i)));
   }
@@ -229,14 +267,10 @@ SB_HD p1p1 ed_mul_var2(const pniels* tab1, const uint32_t* k1_rec, const pniels*
   c = ed_add(p1p1_to_ext(c), vartable_lookup(tab2, recode_digit<4>(k2_rec, nwin - 1)));
 #pragma unroll 1
   for (int i = nwin - 2; i >= 0; i--) {
-    proj p = p1p1_to_proj(c);
-    c = ed_dbl(p.X, p.Y, p.Z);
-    p = p1p1_to_proj(c);
-    c = ed_dbl(p.X, p.Y, p.Z);
-    p = p1p1_to_proj(c);
-    c = ed_dbl(p.X, p.Y, p.Z);
-    p = p1p1_to_proj(c);
-    c = ed_dbl(p.X, p.Y, p.Z);
+    c = pt_dbl(c);
+    c = pt_dbl(c);
+    c = pt_dbl(c);
+    c = pt_dbl(c);
     ext e = p1p1_to_ext(c);
     c = ed_add(e, vartable_lookup(tab1, recode_digit<4>(k1_rec, i)));
     e = p1p1_to_ext(c);
@@ -246,11 +280,22 @@ SB_HD p1p1 ed_mul_var2(const pniels* tab1, const uint32_t* k1_rec, const pniels*
 }
 
 // ------------------------------------------------------------------------------------------
-// fixed-base comb.  Table layout: window j (0..31), entry e (0..128) = e * 256^j * B in affine Niels
-// form, entry 0 = identity; 129 * 32 entries of 96 bytes.  acc += k * B with k offset-recoded (W = 8).
+// fixed-base comb.  Table layout: window j, entry e (0..2^(W-1)) = e * 2^(W*j) * B in affine Niels form,
+// entry 0 = identity; 96 bytes per entry.  acc += k * B with k offset-recoded (W = COMB_BITS).
 // ------------------------------------------------------------------------------------------
-constexpr int COMB_WINDOWS = 32;
-constexpr int COMB_ENTRIES = 129;
+// Window width of the fixed-base comb.  16 bits on the device: 16 additions per scalar and a 50 MB table per
+// generator (16 x 32769 x 96 B) that simply lives in HBM/L2 -- a lookup is 96 bytes per ~4000 cycles of
+// addition, 30 GB/s at full speed.  The CPU test build uses 8 bits (the emulated table build is slow).
+#ifndef SB_COMB_BITS
+#if defined(__CUDACC__)
+#define SB_COMB_BITS 16
+#else
+#define SB_COMB_BITS 8
+#endif
+#endif
+constexpr int COMB_BITS = SB_COMB_BITS;
+constexpr int COMB_WINDOWS = 256 / COMB_BITS;
+constexpr int COMB_ENTRIES = (1 << (COMB_BITS - 1)) + 1;
 
 SB_HD aniels comb_load(const uint32_t* table, int j, int e) {
   const uint4* p = reinterpret_cast<const uint4*>(table) + (size_t)(j * COMB_ENTRIES + e) * 6;
@@ -267,7 +312,7 @@ SB_HD p1p1 ed_comb_add(ext acc, const uint32_t* table, const uint32_t* k_rec) {
   p1p1 c;
 #pragma unroll 1
   for (int j = 0; j < COMB_WINDOWS; j++) {
-    int d = recode_digit<8>(k_rec, j);
+    int d = recode_digit<COMB_BITS>(k_rec, j);
     bool neg = d < 0;
     aniels n = aniels_cneg(comb_load(table, j, neg ? -d : d), neg);
     c = ed_add(acc, n);
@@ -280,7 +325,7 @@ SB_HD p1p1 ed_comb_add(ext acc, const uint32_t* table, const uint32_t* k_rec) {
 
 namespace sb200 {
 
-// One comb-table entry: e * 256^j * B in affine Niels form (entry 0 = identity), written as 24 limbs.
+// One comb-table entry: e * 2^(W*j) * B in affine Niels form (entry 0 = identity), written as 24 limbs.
 // Run once per (j, e) at context creation (init kernel) -- plain double-and-add, speed irrelevant.
 SB_HD void comb_build_entry(const fq& Bu, const fq& Bv, int j, int e, uint32_t* out24) {
   ext base = affine_to_ext(Bu, Bv);
@@ -288,9 +333,9 @@ SB_HD void comb_build_entry(const fq& Bu, const fq& Bv, int j, int e, uint32_t* 
   ext acc = ext_identity();
   // scalar = e << (8*j); walk its bits MSB-first: bits 8*j+7 .. 0
 #pragma unroll 1
-  for (int bit = 8 * j + 7; bit >= 0; bit--) {
+  for (int bit = COMB_BITS * j + COMB_BITS - 1; bit >= 0; bit--) {
     acc = p1p1_to_ext(ed_dbl(acc.X, acc.Y, acc.Z));
-    int eb = bit - 8 * j;
+    int eb = bit - COMB_BITS * j;
     bool set = (eb >= 0) && ((e >> eb) & 1);
     ext sum = p1p1_to_ext(ed_add(acc, nb));
     acc.X = fq_select(acc.X, sum.X, set);

@@ -33,6 +33,10 @@
 
 namespace sb200 {
 
+#ifndef SB_Q1_SHORTCUT
+#define SB_Q1_SHORTCUT 0  // (measured slower: -7% products but a longer dependent chain per row)  replace the m*q[1] product (q[1] = 2^32-1) of every reduction row by two additions
+#endif
+
 struct fq {
   uint32_t v[8];
 };
@@ -165,6 +169,195 @@ SB_HD void blk_red_even_q(uint32_t* x, uint32_t& ytop, uint32_t m, uint32_t q2, 
   c += emu::add_at(x, 8, 6, (uint64_t)m * q6, 0);
   ytop += c;
 #endif
+}
+
+// y[0..7] += m * (q1, q3, q5, q7) with q1 = 2^32 - 1:  m*q1 = (m << 32) - m has low word t0 (= -m) and high word
+// m - (m != 0), so the first product is two additions; three wide products remain.
+SB_HD void blk_red_odd_q(uint32_t* y, uint32_t m, uint32_t t0, uint32_t q3, uint32_t q5, uint32_t q7) {
+#if defined(__CUDA_ARCH__)
+  asm("{\n\t.reg .u32 h;\n\t"
+      "min.u32 h, %8, 1;\n\t"
+      "sub.u32 h, %8, h;\n\t"
+      "add.cc.u32 %0, %0, %9;\n\t"
+      "addc.cc.u32 %1, %1, h;\n\t"
+      "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+      "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+      "madc.lo.cc.u32 %4, %8, %11, %4;\n\t"
+      "madc.hi.cc.u32 %5, %8, %11, %5;\n\t"
+      "madc.lo.cc.u32 %6, %8, %12, %6;\n\t"
+      "madc.hi.u32 %7, %8, %12, %7;\n\t}"
+      : "+r"(y[0]), "+r"(y[1]), "+r"(y[2]), "+r"(y[3]), "+r"(y[4]), "+r"(y[5]), "+r"(y[6]), "+r"(y[7])
+      : "r"(m), "r"(t0), "r"(q3), "r"(q5), "r"(q7));
+#else
+  SB_COUNT(wide, 3);
+  uint32_t hi1 = m - (m != 0 ? 1u : 0u);
+  uint32_t c = emu::add_at(y, 8, 0, ((uint64_t)hi1 << 32) | t0, 0);
+  c += emu::add_at(y, 8, 2, (uint64_t)m * q3, 0);
+  c += emu::add_at(y, 8, 4, (uint64_t)m * q5, 0);
+  c += emu::add_at(y, 8, 6, (uint64_t)m * q7, 0);
+  (void)c;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
+// blocks of the dedicated squaring / separated Montgomery reduction
+// ------------------------------------------------------------------------------------------
+// acc[0..2N) += a * (b0, b1, .. at 64-bit strides), carry out added to acc[2N] (small-valued limb, cannot overflow)
+SB_HD void blk_mac1c(uint32_t* acc, uint32_t a, uint32_t b0) {
+#if defined(__CUDA_ARCH__)
+  asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+      "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+      "addc.u32 %2, %2, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2])
+      : "r"(a), "r"(b0));
+#else
+  SB_COUNT(wide, 1);
+  acc[2] += emu::add_at(acc, 2, 0, (uint64_t)a * b0, 0);
+#endif
+}
+SB_HD void blk_mac2c(uint32_t* acc, uint32_t a, uint32_t b0, uint32_t b1) {
+#if defined(__CUDA_ARCH__)
+  asm("mad.lo.cc.u32 %0, %5, %6, %0;\n\t"
+      "madc.hi.cc.u32 %1, %5, %6, %1;\n\t"
+      "madc.lo.cc.u32 %2, %5, %7, %2;\n\t"
+      "madc.hi.cc.u32 %3, %5, %7, %3;\n\t"
+      "addc.u32 %4, %4, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4])
+      : "r"(a), "r"(b0), "r"(b1));
+#else
+  SB_COUNT(wide, 2);
+  uint32_t c = emu::add_at(acc, 4, 0, (uint64_t)a * b0, 0);
+  c += emu::add_at(acc, 4, 2, (uint64_t)a * b1, 0);
+  acc[4] += c;
+#endif
+}
+SB_HD void blk_mac3c(uint32_t* acc, uint32_t a, uint32_t b0, uint32_t b1, uint32_t b2) {
+#if defined(__CUDA_ARCH__)
+  asm("mad.lo.cc.u32 %0, %7, %8, %0;\n\t"
+      "madc.hi.cc.u32 %1, %7, %8, %1;\n\t"
+      "madc.lo.cc.u32 %2, %7, %9, %2;\n\t"
+      "madc.hi.cc.u32 %3, %7, %9, %3;\n\t"
+      "madc.lo.cc.u32 %4, %7, %10, %4;\n\t"
+      "madc.hi.cc.u32 %5, %7, %10, %5;\n\t"
+      "addc.u32 %6, %6, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6])
+      : "r"(a), "r"(b0), "r"(b1), "r"(b2));
+#else
+  SB_COUNT(wide, 3);
+  uint32_t c = emu::add_at(acc, 6, 0, (uint64_t)a * b0, 0);
+  c += emu::add_at(acc, 6, 2, (uint64_t)a * b1, 0);
+  c += emu::add_at(acc, 6, 4, (uint64_t)a * b2, 0);
+  acc[6] += c;
+#endif
+}
+SB_HD void blk_mac4c(uint32_t* acc, uint32_t a, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
+  blk_mac_even(acc, acc[8], a, b0, b1, b2, b3);
+}
+
+// t[0..15] += (a0^2, a1^2, .., a7^2) at 64-bit strides: one chain of 8 wide products (the total fits 16 limbs)
+SB_HD void blk_sqr_diag(uint32_t* t, const uint32_t* a) {
+#if defined(__CUDA_ARCH__)
+  asm("mad.lo.cc.u32 %0, %16, %16, %0;\n\t"
+      "madc.hi.cc.u32 %1, %16, %16, %1;\n\t"
+      "madc.lo.cc.u32 %2, %17, %17, %2;\n\t"
+      "madc.hi.cc.u32 %3, %17, %17, %3;\n\t"
+      "madc.lo.cc.u32 %4, %18, %18, %4;\n\t"
+      "madc.hi.cc.u32 %5, %18, %18, %5;\n\t"
+      "madc.lo.cc.u32 %6, %19, %19, %6;\n\t"
+      "madc.hi.cc.u32 %7, %19, %19, %7;\n\t"
+      "madc.lo.cc.u32 %8, %20, %20, %8;\n\t"
+      "madc.hi.cc.u32 %9, %20, %20, %9;\n\t"
+      "madc.lo.cc.u32 %10, %21, %21, %10;\n\t"
+      "madc.hi.cc.u32 %11, %21, %21, %11;\n\t"
+      "madc.lo.cc.u32 %12, %22, %22, %12;\n\t"
+      "madc.hi.cc.u32 %13, %22, %22, %13;\n\t"
+      "madc.lo.cc.u32 %14, %23, %23, %14;\n\t"
+      "madc.hi.u32 %15, %23, %23, %15;"
+      : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]),
+        "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+#else
+  SB_COUNT(wide, 8);
+  uint32_t c = 0;
+  for (int i = 0; i < 8; i++) c += emu::add_at(t, 16, 2 * i, (uint64_t)a[i] * a[i], 0);
+  (void)c;
+#endif
+}
+
+// r[0..15] = e[0..15] + (o[0..14] << 32)   (o[k] sits at limb position k + 1); the sum fits 16 limbs
+SB_HD void merge_eo16(uint32_t* r, const uint32_t* e, const uint32_t* o) {
+#if defined(__CUDA_ARCH__)
+  r[0] = e[0];
+  asm("add.cc.u32 %0, %15, %30;\n\t"
+      "addc.cc.u32 %1, %16, %31;\n\t"
+      "addc.cc.u32 %2, %17, %32;\n\t"
+      "addc.cc.u32 %3, %18, %33;\n\t"
+      "addc.cc.u32 %4, %19, %34;\n\t"
+      "addc.cc.u32 %5, %20, %35;\n\t"
+      "addc.cc.u32 %6, %21, %36;\n\t"
+      "addc.cc.u32 %7, %22, %37;\n\t"
+      "addc.cc.u32 %8, %23, %38;\n\t"
+      "addc.cc.u32 %9, %24, %39;\n\t"
+      "addc.cc.u32 %10, %25, %40;\n\t"
+      "addc.cc.u32 %11, %26, %41;\n\t"
+      "addc.cc.u32 %12, %27, %42;\n\t"
+      "addc.cc.u32 %13, %28, %43;\n\t"
+      "addc.u32 %14, %29, %44;"
+      : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(e[8]), "r"(e[9]), "r"(e[10]),
+        "r"(e[11]), "r"(e[12]), "r"(e[13]), "r"(e[14]), "r"(e[15]), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]),
+        "r"(o[5]), "r"(o[6]), "r"(o[7]), "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]), "r"(o[12]), "r"(o[13]), "r"(o[14]));
+#else
+  r[0] = e[0];
+  uint64_t c = 0;
+  for (int i = 1; i < 16; i++) {
+    c += (uint64_t)e[i] + o[i - 1];
+    r[i] = (uint32_t)c;
+    c >>= 32;
+  }
+#endif
+}
+
+// One row of the separated Montgomery reduction, odd half, fused with the fold:
+//   x0 += xf + (tprev != 0);  m = -x0;  y[0..7] += m * (q1, q3, q5, q7) + carry of the fold
+//   (m * q1 by the two-addition shortcut of blk_red_odd_q).
+SB_HD uint32_t blk_fold_red_odd(uint32_t& x0, uint32_t xf, uint32_t tprev, uint32_t* y, uint32_t q1, uint32_t q3,
+                                uint32_t q5, uint32_t q7) {
+  uint32_t m;
+#if defined(__CUDA_ARCH__)
+  asm("{\n\t.reg .u32 t, h;\n\t"
+      "add.cc.u32 t, %11, 0xffffffff;\n\t"
+      "addc.cc.u32 %0, %0, %10;\n\t"
+      "xor.b32 %9, %0, %12;\n\t"
+      "add.u32 %9, %9, 1;\n\t"
+      "min.u32 h, %9, 1;\n\t"
+      "sub.u32 h, %9, h;\n\t"
+      "addc.cc.u32 %1, %1, %0;\n\t"
+      "addc.cc.u32 %2, %2, h;\n\t"
+      "madc.lo.cc.u32 %3, %9, %13, %3;\n\t"
+      "madc.hi.cc.u32 %4, %9, %13, %4;\n\t"
+      "madc.lo.cc.u32 %5, %9, %14, %5;\n\t"
+      "madc.hi.cc.u32 %6, %9, %14, %6;\n\t"
+      "madc.lo.cc.u32 %7, %9, %15, %7;\n\t"
+      "madc.hi.u32 %8, %9, %15, %8;\n\t}"
+      : "+r"(x0), "+r"(y[0]), "+r"(y[1]), "+r"(y[2]), "+r"(y[3]), "+r"(y[4]), "+r"(y[5]), "+r"(y[6]), "+r"(y[7]), "=&r"(m)
+      : "r"(xf), "r"(tprev), "r"(q1), "r"(q3), "r"(q5), "r"(q7));
+#else
+  SB_COUNT(wide, 4);
+  uint64_t t = (uint64_t)x0 + xf + (tprev != 0 ? 1u : 0u);
+  x0 = (uint32_t)t;
+  uint32_t c = (uint32_t)(t >> 32);
+  m = 0u - x0;
+  SB_COUNT(wide, -1);
+  (void)q1;
+  c = emu::add_at(y, 8, 0, ((uint64_t)(m - (m != 0 ? 1u : 0u)) << 32) | x0, c);
+  c += emu::add_at(y, 8, 2, (uint64_t)m * q3, 0);
+  c += emu::add_at(y, 8, 4, (uint64_t)m * q5, 0);
+  c += emu::add_at(y, 8, 6, (uint64_t)m * q7, 0);
+  (void)c;
+#endif
+  return m;
 }
 
 // r = a + b (8 limbs), returns carry
@@ -357,7 +550,7 @@ SB_HD fq fq_select(const fq& a, const fq& b, bool take_b) {
 }
 
 // Montgomery product a * b * 2^-256 mod q, inputs and output canonical (< q).
-// 8 rows x (8 + 7) wide products.
+// 8 rows x (8 + 6) wide products.
 SB_HD fq fq_mul_inl(const fq& a, const fq& b) {
   SB_COUNT(fq_mul, 1);
   uint32_t X[8], Y[8], xf = 0, tprev = 0;
@@ -377,7 +570,11 @@ SB_HD fq fq_mul_inl(const fq& a, const fq& b) {
     // (Two ALU-pipe instructions; a multiply by q1 would cost the saturated FMA-heavy pipe instead.)
     uint32_t m = (tprev ^ q1) + 1u;
     blk_red_even_q(X, Y[7], m, q2, q4, q6);
+#if SB_Q1_SHORTCUT
+    blk_red_odd_q(Y, m, tprev, q3, q5, q7);
+#else
     blk_mac_odd(Y, m, q1, q3, q5, q7);
+#endif
     // divide by 2^32: the odd array becomes the even one; X[1] (+ the carry of the cancelled limb) is
     // folded in by the next row
     xf = X[1];
@@ -402,6 +599,78 @@ SB_HD fq fq_mul_inl(const fq& a, const fq& b) {
   return r;
 }
 
+// Montgomery reduction of a 16-limb T < q * 2^256:  (T_lo + M q) / 2^256 + T_hi, conditional subtraction.
+// M depends on T_lo only, so the 8 rows run on a 9-limb window seeded with T_lo (7 wide products each) and
+// T_hi is added once at the end.
+SB_HD fq mont_reduce16(const uint32_t* t) {
+  uint32_t X[8], Y[8], xf = 0, tprev = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    X[i] = t[i];
+    Y[i] = 0;
+  }
+  const uint32_t q1 = SB_FQ_MOD(1), q2 = SB_FQ_MOD(2), q3 = SB_FQ_MOD(3), q4 = SB_FQ_MOD(4), q5 = SB_FQ_MOD(5),
+                 q6 = SB_FQ_MOD(6), q7 = SB_FQ_MOD(7);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint32_t m = blk_fold_red_odd(X[0], xf, tprev, Y, q1, q3, q5, q7);
+    tprev = X[0];
+    blk_red_even_q(X, Y[7], m, q2, q4, q6);
+    xf = X[1];
+    uint32_t nx[8], ny[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) nx[k] = Y[k];
+#pragma unroll
+    for (int k = 0; k < 6; k++) ny[k] = X[k + 2];
+    ny[6] = 0;
+    ny[7] = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      X[k] = nx[k];
+      Y[k] = ny[k];
+    }
+  }
+  // V = X + xf + (tprev != 0) + (Y << 32) <= q;  result = V + T_hi < 2q
+  fq v, r;
+  uint32_t s[8] = {xf, Y[0], Y[1], Y[2], Y[3], Y[4], Y[5], Y[6]};
+  add8c(v.v, X, s, tprev);
+  add8(r.v, v.v, t + 8);
+  cond_sub_p<FqP>(r.v);
+  return r;
+}
+
+// Dedicated squaring: 28 off-diagonal products (accumulated in an even- and an odd-aligned array so every
+// chain fuses), doubled by a 1-bit funnel shift, plus the 8 diagonal squares in one chain; then the
+// separated reduction.  36 + 56 = 92 wide products instead of 120.
+SB_HD fq fq_sqr_inl(const fq& x) {
+  SB_COUNT(fq_sqr, 1);
+  const uint32_t* a = x.v;
+  uint32_t E[16], O[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) E[i] = O[i] = 0;
+  // row i: a_i * a_j for j > i; j - i odd -> odd-aligned array (index = position - 1), even -> even-aligned
+  blk_mac4c(O + 0, a[0], a[1], a[3], a[5], a[7]);
+  blk_mac3c(E + 2, a[0], a[2], a[4], a[6]);
+  blk_mac3c(O + 2, a[1], a[2], a[4], a[6]);
+  blk_mac3c(E + 4, a[1], a[3], a[5], a[7]);
+  blk_mac3c(O + 4, a[2], a[3], a[5], a[7]);
+  blk_mac2c(E + 6, a[2], a[4], a[6]);
+  blk_mac2c(O + 6, a[3], a[4], a[6]);
+  blk_mac2c(E + 8, a[3], a[5], a[7]);
+  blk_mac2c(O + 8, a[4], a[5], a[7]);
+  blk_mac1c(E + 10, a[4], a[6]);
+  blk_mac1c(O + 10, a[5], a[6]);
+  blk_mac1c(E + 12, a[5], a[7]);
+  blk_mac1c(O + 12, a[6], a[7]);
+  uint32_t S[16], T[16];
+  merge_eo16(S, E, O);
+  T[0] = S[0] << 1;
+#pragma unroll
+  for (int i = 1; i < 16; i++) T[i] = (S[i] << 1) | (S[i - 1] >> 31);
+  blk_sqr_diag(T, a);
+  return mont_reduce16(T);
+}
+
 // The kernels call the multiplier out of line: a verification is ~3600 products, and with every one
 // inlined the kernel is 650 KB of SASS and stalls on instruction fetch (ncu: stall_no_instruction was the
 // top stall reason).  Arguments and result travel in registers (no stack traffic).
@@ -410,6 +679,7 @@ SB_HD fq fq_mul_inl(const fq& a, const fq& b) {
 #endif
 #if defined(__CUDACC__) && SB_MUL_NOINLINE
 static __device__ __noinline__ fq fq_mul_ool(fq a, fq b) { return fq_mul_inl(a, b); }
+static __device__ __noinline__ fq fq_sqr_ool(fq a) { return fq_sqr_inl(a); }
 #endif
 SB_HD fq fq_mul(const fq& a, const fq& b) {
 #if defined(__CUDA_ARCH__) && SB_MUL_NOINLINE
@@ -418,11 +688,12 @@ SB_HD fq fq_mul(const fq& a, const fq& b) {
   return fq_mul_inl(a, b);
 #endif
 }
-
 SB_HD fq fq_sqr(const fq& a) {
-  SB_COUNT(fq_sqr, 1);
-  SB_COUNT(fq_mul, -1);
-  return fq_mul(a, a);
+#if defined(__CUDA_ARCH__) && SB_MUL_NOINLINE
+  return fq_sqr_ool(a);
+#else
+  return fq_sqr_inl(a);
+#endif
 }
 
 SB_HD fq fq_to_mont(const fq& a) {

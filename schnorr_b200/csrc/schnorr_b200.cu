@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(TPB, MIN_CTAS) k_run(const KArgs a) {
 
 __global__ void __launch_bounds__(TPB) k_comb_build(uint32_t* table, int which) {
   int t = blockIdx.x * TPB + threadIdx.x;
-  if (t >= COMB_WINDOWS * COMB_ENTRIES) return;
+  if (t >= COMB_WINDOWS * COMB_ENTRIES) return;  // 524 304 entries at 16-bit windows
   const fq gu = {SB200_G_U_INIT}, gv = {SB200_G_V_INIT}, hu = {SB200_GP_U_INIT}, hv = {SB200_GP_V_INIT};
   comb_build_entry(which ? hu : gu, which ? hv : gv, t / COMB_ENTRIES, t % COMB_ENTRIES, table + (size_t)t * 24);
 }

@@ -13,6 +13,7 @@ extern "C" {
 void h_counts_reset() { emu::cnt() = {0, 0, 0, 0, 0}; }
 void h_counts_get(unsigned long long* o) { auto& c = emu::cnt(); o[0] = c.wide; o[1] = c.fq_mul; o[2] = c.fq_sqr; o[3] = c.fq_addsub; o[4] = c.fr_mul; }
 void h_fq_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { S(r, fq_mul(L(a), L(b))); }
+void h_fq_sqr(const uint32_t* a, uint32_t* r) { S(r, fq_sqr(L(a))); }
 void h_fq_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { S(r, fq_add(L(a), L(b))); }
 void h_fq_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { S(r, fq_sub(L(a), L(b))); }
 void h_fq_inv(const uint32_t* a, uint32_t* r) { S(r, fq_inv(L(a))); }
