@@ -47,8 +47,8 @@ struct fq {
 #if !defined(__CUDA_ARCH__)
 namespace emu {
 // op counters of the host (test) build: the roofline's "work per tuple" is counted, not estimated
-struct counters { unsigned long long wide, fq_mul, fq_sqr, fq_addsub, fr_mul; };
-inline counters& cnt() { static thread_local counters c = {0, 0, 0, 0, 0}; return c; }
+struct counters { unsigned long long wide, fq_mul, fq_sqr, fq_addsub, fr_mul, fq_dot5; };
+inline counters& cnt() { static thread_local counters c = {0, 0, 0, 0, 0, 0}; return c; }
 #define SB_COUNT(field, k) (::sb200::emu::cnt().field += (k))
 // acc[0..n) += addend (little-endian limbs) starting at limb `at`; returns carry out of limb n-1
 static inline uint32_t add_at(uint32_t* acc, int n, int at, uint64_t val, uint32_t cin) {
@@ -671,6 +671,127 @@ SB_HD fq fq_sqr_inl(const fq& x) {
   return mont_reduce16(T);
 }
 
+// ------------------------------------------------------------------------------------------
+// Lazy-reduced dot product  sum_j c_j * s_j  (n <= 5 terms): n full products (64 wide each) accumulated as
+// one 17-limb integer and ONE Montgomery reduction (56 wide), instead of n * 120.  Used by the Hades MDS
+// layers.  5 q^2 < 2^513, result before the final subtractions < q + 5 q^2 / 2^256 < 3.27 q.
+// ------------------------------------------------------------------------------------------
+// T[0..15] = a * b : schoolbook product in an even- and an odd-aligned array (all chains fuse; every carry
+// lands on a limb that holds at most earlier carries), merged once.
+SB_HD void mul_wide16(uint32_t* T, const uint32_t* a, const uint32_t* b) {
+  uint32_t E[18], O[18];
+#pragma unroll
+  for (int i = 0; i < 18; i++) E[i] = O[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    if ((i & 1) == 0) {
+      blk_mac4c(E + i, a[i], b[0], b[2], b[4], b[6]);
+      blk_mac4c(O + i, a[i], b[1], b[3], b[5], b[7]);
+    } else {
+      blk_mac4c(O + i - 1, a[i], b[0], b[2], b[4], b[6]);
+      blk_mac4c(E + i + 1, a[i], b[1], b[3], b[5], b[7]);
+    }
+  }
+  merge_eo16(T, E, O);
+}
+
+// S[0..16] += T[0..15]
+SB_HD void acc17(uint32_t* S, const uint32_t* T) {
+#if defined(__CUDA_ARCH__)
+  asm("add.cc.u32 %0, %0, %17;\n\t"
+      "addc.cc.u32 %1, %1, %18;\n\t"
+      "addc.cc.u32 %2, %2, %19;\n\t"
+      "addc.cc.u32 %3, %3, %20;\n\t"
+      "addc.cc.u32 %4, %4, %21;\n\t"
+      "addc.cc.u32 %5, %5, %22;\n\t"
+      "addc.cc.u32 %6, %6, %23;\n\t"
+      "addc.cc.u32 %7, %7, %24;\n\t"
+      "addc.cc.u32 %8, %8, %25;\n\t"
+      "addc.cc.u32 %9, %9, %26;\n\t"
+      "addc.cc.u32 %10, %10, %27;\n\t"
+      "addc.cc.u32 %11, %11, %28;\n\t"
+      "addc.cc.u32 %12, %12, %29;\n\t"
+      "addc.cc.u32 %13, %13, %30;\n\t"
+      "addc.cc.u32 %14, %14, %31;\n\t"
+      "addc.cc.u32 %15, %15, %32;\n\t"
+      "addc.u32 %16, %16, 0;"
+      : "+r"(S[0]), "+r"(S[1]), "+r"(S[2]), "+r"(S[3]), "+r"(S[4]), "+r"(S[5]), "+r"(S[6]), "+r"(S[7]), "+r"(S[8]),
+        "+r"(S[9]), "+r"(S[10]), "+r"(S[11]), "+r"(S[12]), "+r"(S[13]), "+r"(S[14]), "+r"(S[15]), "+r"(S[16])
+      : "r"(T[0]), "r"(T[1]), "r"(T[2]), "r"(T[3]), "r"(T[4]), "r"(T[5]), "r"(T[6]), "r"(T[7]), "r"(T[8]), "r"(T[9]),
+        "r"(T[10]), "r"(T[11]), "r"(T[12]), "r"(T[13]), "r"(T[14]), "r"(T[15]));
+#else
+  uint64_t c = 0;
+  for (int i = 0; i < 16; i++) {
+    c += (uint64_t)S[i] + T[i];
+    S[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  S[16] += (uint32_t)c;
+#endif
+}
+
+// Montgomery reduction of a 17-limb S < 5 q^2 to the canonical representative.
+SB_HD fq mont_reduce17(const uint32_t* S) {
+  uint32_t X[8], Y[8], xf = 0, tprev = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    X[i] = S[i];
+    Y[i] = 0;
+  }
+  const uint32_t q1 = SB_FQ_MOD(1), q2 = SB_FQ_MOD(2), q3 = SB_FQ_MOD(3), q4 = SB_FQ_MOD(4), q5 = SB_FQ_MOD(5),
+                 q6 = SB_FQ_MOD(6), q7 = SB_FQ_MOD(7);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint32_t m = blk_fold_red_odd(X[0], xf, tprev, Y, q1, q3, q5, q7);
+    tprev = X[0];
+    blk_red_even_q(X, Y[7], m, q2, q4, q6);
+    xf = X[1];
+    uint32_t nx[8], ny[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) nx[k] = Y[k];
+#pragma unroll
+    for (int k = 0; k < 6; k++) ny[k] = X[k + 2];
+    ny[6] = 0;
+    ny[7] = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      X[k] = nx[k];
+      Y[k] = ny[k];
+    }
+  }
+  fq v, r;
+  uint32_t s[8] = {xf, Y[0], Y[1], Y[2], Y[3], Y[4], Y[5], Y[6]};
+  add8c(v.v, X, s, tprev);                   // V0 <= q
+  uint32_t top = S[16] + add8(r.v, v.v, S + 8);  // 9-limb value r + top * 2^256 < 3.27 q
+  // >= 2q ?  (2q < 2^256)
+  uint32_t t[8], q2x[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) q2x[i] = (FqP::p(i) << 1) | (i ? FqP::p(i - 1) >> 31 : 0u);
+  uint32_t borrow = sub8(t, r.v, q2x);
+  bool ge = (top != 0) | (borrow == 0);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = ge ? t[i] : r.v[i];
+  cond_sub_p<FqP>(r.v);
+  return r;
+}
+
+// sum_{j<5} c_j * s_j with the constants c_j read through `cst` (5 consecutive field elements)
+SB_HD fq fq_dot5_inl(const uint32_t (*cst)[8], const fq& s0, const fq& s1, const fq& s2, const fq& s3, const fq& s4) {
+  SB_COUNT(fq_dot5, 1);
+  uint32_t S[17], T[16], c[8];
+#pragma unroll
+  for (int i = 0; i < 17; i++) S[i] = 0;
+  const fq* sv[5] = {&s0, &s1, &s2, &s3, &s4};
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) c[i] = cst[j][i];
+    mul_wide16(T, sv[j]->v, c);
+    acc17(S, T);
+  }
+  return mont_reduce17(S);
+}
+
 // The kernels call the multiplier out of line: a verification is ~3600 products, and with every one
 // inlined the kernel is 650 KB of SASS and stalls on instruction fetch (ncu: stall_no_instruction was the
 // top stall reason).  Arguments and result travel in registers (no stack traffic).
@@ -680,12 +801,22 @@ SB_HD fq fq_sqr_inl(const fq& x) {
 #if defined(__CUDACC__) && SB_MUL_NOINLINE
 static __device__ __noinline__ fq fq_mul_ool(fq a, fq b) { return fq_mul_inl(a, b); }
 static __device__ __noinline__ fq fq_sqr_ool(fq a) { return fq_sqr_inl(a); }
+static __device__ __noinline__ fq fq_dot5_ool(const uint32_t (*cst)[8], fq s0, fq s1, fq s2, fq s3, fq s4) {
+  return fq_dot5_inl(cst, s0, s1, s2, s3, s4);
+}
 #endif
 SB_HD fq fq_mul(const fq& a, const fq& b) {
 #if defined(__CUDA_ARCH__) && SB_MUL_NOINLINE
   return fq_mul_ool(a, b);
 #else
   return fq_mul_inl(a, b);
+#endif
+}
+SB_HD fq fq_dot5(const uint32_t (*cst)[8], const fq& s0, const fq& s1, const fq& s2, const fq& s3, const fq& s4) {
+#if defined(__CUDA_ARCH__) && SB_MUL_NOINLINE
+  return fq_dot5_ool(cst, s0, s1, s2, s3, s4);
+#else
+  return fq_dot5_inl(cst, s0, s1, s2, s3, s4);
 #endif
 }
 SB_HD fq fq_sqr(const fq& a) {

@@ -47,7 +47,17 @@ SB_HD fq fq_pow5(const fq& x) {
 }
 
 // s <- M * s with M a dense 5x5 matrix in constant memory (row-major)
-#define SB_MATMUL5(s, mat)                                              \
+// (each row is one lazily reduced dot product: 5 x 64 + 56 wide products instead of 5 x 120)
+#define SB_MATMUL5(s, mat)                                                                  \
+  do {                                                                                      \
+    fq _r[5];                                                                               \
+    _Pragma("unroll") for (int _k = 0; _k < 5; _k++)                                        \
+        _r[_k] = fq_dot5(&SB_CONST(mat)[_k * 5], s[0], s[1], s[2], s[3], s[4]);             \
+    _Pragma("unroll") for (int _k = 0; _k < 5; _k++) s[_k] = _r[_k];                        \
+  } while (0)
+
+// plain version (one reduction per product) for the reference-shaped dense permutation
+#define SB_MATMUL5_PLAIN(s, mat)                                        \
   do {                                                                  \
     fq _r[5];                                                           \
     _Pragma("unroll 1") for (int _k = 0; _k < 5; _k++) {                \
@@ -59,26 +69,27 @@ SB_HD fq fq_pow5(const fq& x) {
     _Pragma("unroll") for (int _k = 0; _k < 5; _k++) s[_k] = _r[_k];    \
   } while (0)
 
+template <bool LAZY = true>
 SB_HD void hades_full_round(fq* s, int rc_base) {
 #pragma unroll
   for (int k = 0; k < 5; k++) s[k] = fq_pow5(fq_add(s[k], ld8(SB_CONST(hades_rc)[rc_base + k])));
-  SB_MATMUL5(s, hades_mds);
+  if (LAZY) SB_MATMUL5(s, hades_mds); else SB_MATMUL5_PLAIN(s, hades_mds);
 }
 
 // Reference-shaped permutation (ScalarStrategy::perm of dusk-hades): used by parity tests.
 SB_HD void hades_perm_dense(fq* s) {
   int rc = 0;
 #pragma unroll 1
-  for (int r = 0; r < 4; r++, rc += 5) hades_full_round(s, rc);
+  for (int r = 0; r < 4; r++, rc += 5) hades_full_round<false>(s, rc);
 #pragma unroll 1
   for (int r = 0; r < 59; r++, rc += 5) {
 #pragma unroll
     for (int k = 0; k < 5; k++) s[k] = fq_add(s[k], ld8(SB_CONST(hades_rc)[rc + k]));
     s[4] = fq_pow5(s[4]);
-    SB_MATMUL5(s, hades_mds);
+    SB_MATMUL5_PLAIN(s, hades_mds);
   }
 #pragma unroll 1
-  for (int r = 0; r < 4; r++, rc += 5) hades_full_round(s, rc);
+  for (int r = 0; r < 4; r++, rc += 5) hades_full_round<false>(s, rc);
 }
 
 // Production permutation: sparse partial rounds.
@@ -92,12 +103,9 @@ SB_HD void hades_perm(fq* s) {
   for (int t = 0; t < 59; t++) {
     const uint32_t(*c)[8] = &SB_CONST(hades_sparse)[t * 11];
     s[4] = fq_pow5(fq_add(s[4], ld8(c[0])));
-    fq np = fq_mul(ld8(c[1 + 4]), s[4]);
+    fq np = fq_dot5(&c[1], s[0], s[1], s[2], s[3], s[4]);  // row . state, one reduction
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      np = fq_add(np, fq_mul(ld8(c[1 + j]), s[j]));
-      s[j] = fq_add(s[j], fq_mul(ld8(c[6 + j]), s[4]));
-    }
+    for (int j = 0; j < 4; j++) s[j] = fq_add(s[j], fq_mul(ld8(c[6 + j]), s[4]));
     s[4] = np;
   }
   SB_MATMUL5(s, hades_post);

@@ -10,10 +10,13 @@ static fq L(const uint32_t* p) { fq r; memcpy(r.v, p, 32); return r; }
 static void S(uint32_t* p, const fq& a) { memcpy(p, a.v, 32); }
 
 extern "C" {
-void h_counts_reset() { emu::cnt() = {0, 0, 0, 0, 0}; }
-void h_counts_get(unsigned long long* o) { auto& c = emu::cnt(); o[0] = c.wide; o[1] = c.fq_mul; o[2] = c.fq_sqr; o[3] = c.fq_addsub; o[4] = c.fr_mul; }
+void h_counts_reset() { emu::cnt() = {0, 0, 0, 0, 0, 0}; }
+void h_counts_get(unsigned long long* o) { auto& c = emu::cnt(); o[0] = c.wide; o[1] = c.fq_mul; o[2] = c.fq_sqr; o[3] = c.fq_addsub; o[4] = c.fr_mul; o[5] = c.fq_dot5; }
 void h_fq_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { S(r, fq_mul(L(a), L(b))); }
 void h_fq_sqr(const uint32_t* a, uint32_t* r) { S(r, fq_sqr(L(a))); }
+void h_fq_dot5(const uint32_t* c40, const uint32_t* s40, uint32_t* r) {
+  S(r, fq_dot5(reinterpret_cast<const uint32_t(*)[8]>(c40), L(s40), L(s40 + 8), L(s40 + 16), L(s40 + 24), L(s40 + 32)));
+}
 void h_fq_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { S(r, fq_add(L(a), L(b))); }
 void h_fq_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { S(r, fq_sub(L(a), L(b))); }
 void h_fq_inv(const uint32_t* a, uint32_t* r) { S(r, fq_inv(L(a))); }

@@ -42,6 +42,20 @@ def test_fq_fr(lib):
             lib.h_fr_mul(H.ptr(H.limbs(a)), H.ptr(H.limbs(b)), H.ptr(out)); assert H.to_int(out) == a * b % R
 
 
+def test_lazy_dot5_extremes(lib):
+    """sum of 5 products with one reduction: worst case 5 (q-1)^2 needs the 17th limb and both final subtractions"""
+    rnd = random.Random(7)
+    out = np.zeros(8, np.uint32)
+    rinv = pow(H.RADIX, -1, Q)
+    cases = [([Q - 1] * 5, [Q - 1] * 5), ([Q - 1] * 5, [Q - 2, 1, 0, Q - 1, 2]), ([0] * 5, [Q - 1] * 5), ([1, 0, 0, 0, 0], [5, 0, 0, 0, 0])]
+    cases += [([rnd.randrange(Q) for _ in range(5)], [rnd.randrange(Q) for _ in range(5)]) for _ in range(200)]
+    cases += [([Q - 1 - rnd.randrange(1 << 40) for _ in range(5)], [Q - 1 - rnd.randrange(1 << 40) for _ in range(5)]) for _ in range(50)]
+    for c, s in cases:
+        cb = np.concatenate([H.limbs(x) for x in c]); sb = np.concatenate([H.limbs(x) for x in s])
+        lib.h_fq_dot5(H.ptr(cb), H.ptr(sb), H.ptr(out))
+        assert H.to_int(out) == sum(a * b for a, b in zip(c, s)) * rinv % Q
+
+
 @pytest.mark.parametrize("dense", [1, 0])
 def test_hades(lib, dense):
     rnd = random.Random(2)
