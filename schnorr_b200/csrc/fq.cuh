@@ -799,8 +799,18 @@ SB_HD fq fq_dot5_inl(const uint32_t (*cst)[8], const fq& s0, const fq& s1, const
 #define SB_MUL_NOINLINE 1
 #endif
 #if defined(__CUDACC__) && SB_MUL_NOINLINE
+#ifndef SB_MUL_BYPTR
+#define SB_MUL_BYPTR 0  // experiment: operands through local memory instead of the register ABI
+#endif
+#if SB_MUL_BYPTR
+static __device__ __noinline__ void fq_mul_ptr(fq* r, const fq* a, const fq* b) { *r = fq_mul_inl(*a, *b); }
+static __device__ __noinline__ void fq_sqr_ptr(fq* r, const fq* a) { *r = fq_sqr_inl(*a); }
+static __device__ __forceinline__ fq fq_mul_ool(const fq& a, const fq& b) { fq r; fq_mul_ptr(&r, &a, &b); return r; }
+static __device__ __forceinline__ fq fq_sqr_ool(const fq& a) { fq r; fq_sqr_ptr(&r, &a); return r; }
+#else
 static __device__ __noinline__ fq fq_mul_ool(fq a, fq b) { return fq_mul_inl(a, b); }
 static __device__ __noinline__ fq fq_sqr_ool(fq a) { return fq_sqr_inl(a); }
+#endif
 static __device__ __noinline__ fq fq_dot5_ool(const uint32_t (*cst)[8], fq s0, fq s1, fq s2, fq s3, fq s4) {
   return fq_dot5_inl(cst, s0, s1, s2, s3, s4);
 }
