@@ -103,6 +103,32 @@ int sb200_keygen_double(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_
 int sb200_keygen_vargen(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* sk, const uint32_t* generator,
                         uint32_t* pk_out);
 
+/* ---- wire formats on the device (the reference's serialised forms) ---------------------
+ * bytes32 point  = JubJubAffine::to_bytes (v little-endian, bit 255 = low bit of u);
+ * sig64          = Signature::to_bytes = u (32 B canonical) || compressed R   /root/reference/src/signatures.rs:106-123
+ * msg32 / sk32   = BlsScalar::to_bytes / SecretKey::to_bytes (32 B canonical little-endian)
+ * `flags` here may only carry SB200_DEVICE_PTRS. */
+/* JubJubAffine::from_bytes for n points; ok bit i = 0 where the reference returns None (v >= q or not on the
+ * curve).  No subgroup check, as in the reference (/root/reference/src/keys/public.rs:94-100). */
+int sb200_points_decompress(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* bytes32, uint32_t* points_out,
+                            uint32_t* ok_bitmap);
+/* JubJubAffine::from(point).to_bytes(); points per SB200_POINTS_AFFINE / PROJECTIVE in flags */
+int sb200_points_compress(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* points, uint8_t* bytes32_out);
+/* Field::random's from_bytes_wide on n 64-byte draws: field 0 -> JubJubScalar (canonical limbs),
+ * field 1 -> BlsScalar (Montgomery limbs).  /root/reference/src/keys/secret.rs:83,155 */
+int sb200_scalars_from_wide(sb200_ctx* ctx, int64_t n, uint32_t flags, int field, const uint8_t* wide64, uint32_t* out);
+/* canonical <-> Montgomery limbs of n field elements (BlsScalar::from_bytes / to_bytes minus the range check) */
+int sb200_fq_to_mont(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* in, uint32_t* out);
+int sb200_fq_from_mont(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* in, uint32_t* out);
+/* PublicKey::from_bytes(pk)?.verify(&Signature::from_bytes(sig)?, BlsScalar::from_bytes(msg)?) for n tuples.
+ * invalid bit i = 1 where any of the three from_bytes would return Err(InvalidData); its verdict bit is 0.
+ * `invalid` may be NULL. */
+int sb200_verify_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* pk32, const uint8_t* sig64,
+                       const uint8_t* msg32, uint32_t* verdicts, uint32_t* invalid);
+/* SecretKey::from_bytes(sk).sign(nonce, BlsScalar::from_bytes(msg)).to_bytes() for n tuples */
+int sb200_sign_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* sk32, const uint8_t* msg32,
+                     const uint8_t* nonce32, uint8_t* sig64_out);
+
 /* Building-block probes for the parity tests (same kernels' device functions, one element per thread).
  * op: 0 mul (Montgomery product), 1 add, 2 sub, 3 inverse (b ignored), 4 square, 5 to_mont, 6 from_mont */
 int sb200_dbg_fq(sb200_ctx* ctx, int64_t n, int op, const uint32_t* a, const uint32_t* b, uint32_t* out);

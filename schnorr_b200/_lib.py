@@ -55,6 +55,13 @@ def load_library() -> ctypes.CDLL:
         "sb200_keygen": (ci, [vp, i64, u32] + [u32p] * 2),
         "sb200_keygen_double": (ci, [vp, i64, u32] + [u32p] * 3),
         "sb200_keygen_vargen": (ci, [vp, i64, u32] + [u32p] * 3),
+        "sb200_points_decompress": (ci, [vp, i64, u32] + [u32p] * 3),
+        "sb200_points_compress": (ci, [vp, i64, u32] + [u32p] * 2),
+        "sb200_scalars_from_wide": (ci, [vp, i64, u32, ci] + [u32p] * 2),
+        "sb200_fq_to_mont": (ci, [vp, i64, u32] + [u32p] * 2),
+        "sb200_fq_from_mont": (ci, [vp, i64, u32] + [u32p] * 2),
+        "sb200_verify_bytes": (ci, [vp, i64, u32] + [u32p] * 5),
+        "sb200_sign_bytes": (ci, [vp, i64, u32] + [u32p] * 4),
         "sb200_dbg_fq": (ci, [vp, i64, ci] + [u32p] * 3),
         "sb200_dbg_fr_mul": (ci, [vp, i64] + [u32p] * 3),
         "sb200_dbg_hades": (ci, [vp, i64, ci, u32p]),
@@ -71,7 +78,8 @@ EXPORTED_SYMBOLS = [
     "sb200_init", "sb200_destroy", "sb200_strerror", "sb200_last_error", "sb200_device_count", "sb200_set_stream",
     "sb200_launch_count", "sb200_host_alloc", "sb200_host_free", "sb200_verify", "sb200_verify_double",
     "sb200_verify_vargen", "sb200_sign", "sb200_sign_double", "sb200_sign_vargen", "sb200_keygen",
-    "sb200_keygen_double", "sb200_keygen_vargen", "sb200_dbg_fq", "sb200_dbg_fr_mul", "sb200_dbg_hades",
+    "sb200_keygen_double", "sb200_keygen_vargen", "sb200_points_decompress", "sb200_points_compress",
+    "sb200_scalars_from_wide", "sb200_fq_to_mont", "sb200_fq_from_mont", "sb200_verify_bytes", "sb200_sign_bytes", "sb200_dbg_fq", "sb200_dbg_fr_mul", "sb200_dbg_hades",
     "sb200_dbg_scalar_mul",
 ]
 
@@ -224,6 +232,70 @@ class Engine:
         pk = aligned_empty((n, 16))
         self.call("keygen_vargen", n, fl, sk.ctypes.data, gen.ctypes.data, pk.ctypes.data)
         return pk
+
+    # ---- wire formats (bytes in / bytes out) ---------------------------------------------------------
+    @staticmethod
+    def _bytes_arr(b, width: int, name: str) -> np.ndarray:
+        a = np.frombuffer(b, dtype=np.uint8) if isinstance(b, (bytes, bytearray, memoryview)) else np.asarray(b)
+        a = a.view(np.uint8).reshape(-1, width)
+        out = aligned_empty((a.shape[0], width), dtype=np.uint8)
+        out[...] = a
+        return out
+
+    def points_decompress(self, data):
+        """n x 32 bytes -> ([n,16] affine Montgomery limbs, ok[n])"""
+        b = self._bytes_arr(data, 32, "bytes")
+        n = b.shape[0]
+        pts = aligned_empty((n, 16))
+        bm = aligned_empty(((n + 31) // 32,)); bm[...] = 0
+        self.call("points_decompress", n, 0, b.ctypes.data, pts.ctypes.data, bm.ctypes.data)
+        return pts, self._unpack_bits(bm, n)
+
+    def points_compress(self, points, affine=True):
+        n = np.asarray(points).size // self._pw(affine)
+        p = _arr(points, self._pw(affine), n, "points")
+        out = aligned_empty((n, 32), dtype=np.uint8)
+        self.call("points_compress", n, POINTS_AFFINE if affine else POINTS_PROJECTIVE, p.ctypes.data, out.ctypes.data)
+        return out
+
+    def scalars_from_wide(self, wide, field: int):
+        """n x 64 bytes -> [n,8]: field 0 = JubJubScalar (canonical), 1 = BlsScalar (Montgomery)"""
+        b = self._bytes_arr(wide, 64, "wide")
+        n = b.shape[0]
+        out = aligned_empty((n, 8))
+        rc = self._lib.sb200_scalars_from_wide(self._h, n, 0, field, b.ctypes.data, out.ctypes.data)
+        self._check(rc, "scalars_from_wide")
+        return out
+
+    def fq_to_mont(self, a):
+        n = np.asarray(a).size // 8
+        a = _arr(a, 8, n, "a")
+        out = aligned_empty((n, 8))
+        self.call("fq_to_mont", n, 0, a.ctypes.data, out.ctypes.data)
+        return out
+
+    def fq_from_mont(self, a):
+        n = np.asarray(a).size // 8
+        a = _arr(a, 8, n, "a")
+        out = aligned_empty((n, 8))
+        self.call("fq_from_mont", n, 0, a.ctypes.data, out.ctypes.data)
+        return out
+
+    def verify_bytes(self, pk, sig, msg):
+        """pk n x 32, sig n x 64, msg n x 32 (canonical) -> (verdict[n], invalid[n])"""
+        pk, sig, msg = self._bytes_arr(pk, 32, "pk"), self._bytes_arr(sig, 64, "sig"), self._bytes_arr(msg, 32, "msg")
+        n = pk.shape[0]
+        bm = aligned_empty(((n + 31) // 32,)); bm[...] = 0
+        inv = aligned_empty(((n + 31) // 32,)); inv[...] = 0
+        self.call("verify_bytes", n, 0, pk.ctypes.data, sig.ctypes.data, msg.ctypes.data, bm.ctypes.data, inv.ctypes.data)
+        return self._unpack_bits(bm, n), self._unpack_bits(inv, n)
+
+    def sign_bytes(self, sk, msg, nonce):
+        sk, msg, nonce = self._bytes_arr(sk, 32, "sk"), self._bytes_arr(msg, 32, "msg"), self._bytes_arr(nonce, 32, "nonce")
+        n = sk.shape[0]
+        out = aligned_empty((n, 64), dtype=np.uint8)
+        self.call("sign_bytes", n, 0, sk.ctypes.data, msg.ctypes.data, nonce.ctypes.data, out.ctypes.data)
+        return out
 
     # ---- building-block probes --------------------------------------------------------------------
     def dbg_fq(self, op: int, a, b=None):

@@ -17,7 +17,7 @@
 #include <vector>
 
 #include "../../include/schnorr_b200.h"
-#include "core.cuh"
+#include "wire.cuh"
 
 using namespace sb200;
 
@@ -35,7 +35,8 @@ constexpr int64_t CHUNK = 1 << 18;  // tuples per pipeline stage
 
 enum Op : int {
   OP_VERIFY = 0, OP_VERIFY_DOUBLE, OP_VERIFY_VARGEN, OP_SIGN, OP_SIGN_DOUBLE, OP_SIGN_VARGEN,
-  OP_KEYGEN, OP_KEYGEN_DOUBLE, OP_KEYGEN_VARGEN, OP_DBG_FQ, OP_DBG_FR_MUL, OP_DBG_HADES, OP_DBG_SMUL
+  OP_KEYGEN, OP_KEYGEN_DOUBLE, OP_KEYGEN_VARGEN, OP_DBG_FQ, OP_DBG_FR_MUL, OP_DBG_HADES, OP_DBG_SMUL,
+  OP_DECOMPRESS, OP_COMPRESS, OP_FROM_WIDE, OP_VERIFY_BYTES, OP_SIGN_BYTES
 };
 
 struct KArgs {
@@ -194,6 +195,72 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
     if (active) stg_point(a.out[0], i, u, v);
     return;
   }
+  if (OP == OP_DECOMPRESS) {  // in: bytes32 -> out0: affine points, bitmap: ok
+    uint32_t b[8];
+    fq u, v;
+    ldg_scalar(a.in[0] + i * 8, b);
+    bool ok = point_decompress(b, u, v);
+    unsigned word = __ballot_sync(0xffffffffu, ok && active);
+    if ((threadIdx.x & 31) == 0 && active) a.bitmap[i >> 5] = word;
+    if (active) stg_point(a.out[0], i, u, v);
+    return;
+  }
+  if (OP == OP_COMPRESS) {  // in: points -> out0: bytes32
+    point_in p = ldg_point(a.in[0], i, aff);
+    fq u, v;
+    point_to_affine(p, u, v);
+    uint32_t b[8];
+    point_compress(u, v, b);
+    if (active) stg8(a.out[0] + i * 8, b);
+    return;
+  }
+  if (OP == OP_FROM_WIDE) {  // in: 64-byte draws -> out0: scalar (aux 0: mod r canonical, aux 1: mod q Montgomery)
+    uint32_t w[16], r[8];
+    ldg_scalar(a.in[0] + i * 16, w);
+    ldg_scalar(a.in[0] + i * 16 + 8, w + 8);
+    if (a.aux == 0) {
+      fr_from_wide(w, r);
+    } else {
+      fq x = fq_from_wide(w);
+#pragma unroll
+      for (int k = 0; k < 8; k++) r[k] = x.v[k];
+    }
+    if (active) stg8(a.out[0] + i * 8, r);
+    return;
+  }
+  if (OP == OP_VERIFY_BYTES) {  // in: pk32, sig64, msg32 -> bitmap: verdicts, out0 (as bitmap): invalid
+    uint32_t pk[8], sig[16], m[8];
+    ldg_scalar(a.in[0] + i * 8, pk);
+    ldg_scalar(a.in[1] + i * 16, sig);
+    ldg_scalar(a.in[1] + i * 16 + 8, sig + 8);
+    ldg_scalar(a.in[2] + i * 8, m);
+    bool invalid;
+    bool ok = verify_bytes_core(pk, sig, m, a.combG, invalid);
+    unsigned word = __ballot_sync(0xffffffffu, ok && active), inv = __ballot_sync(0xffffffffu, invalid && active);
+    if ((threadIdx.x & 31) == 0 && active) {
+      a.bitmap[i >> 5] = word;
+      if (a.out[0]) a.out[0][i >> 5] = inv;
+    }
+    return;
+  }
+  if (OP == OP_SIGN_BYTES) {  // in: sk32, msg32 (canonical), nonce32 -> out0: sig64 = u || compress(R)
+    uint32_t sk[8], nonce[8], mb[8], u[8], sig[16];
+    fq Ru, Rv, mc;
+    ldg_scalar(a.in[0] + i * 8, sk);
+    ldg_scalar(a.in[1] + i * 8, mb);
+    ldg_scalar(a.in[2] + i * 8, nonce);
+#pragma unroll
+    for (int k = 0; k < 8; k++) mc.v[k] = mb[k];
+    sign_core(sk, nonce, fq_to_mont(mc), a.combG, u, Ru, Rv, c);
+#pragma unroll
+    for (int k = 0; k < 8; k++) sig[k] = u[k];
+    point_compress(Ru, Rv, sig + 8);
+    if (active) {
+      stg8(a.out[0] + i * 16, sig);
+      stg8(a.out[0] + i * 16 + 8, sig + 8);
+    }
+    return;
+  }
 }
 
 __global__ void __launch_bounds__(TPB) k_comb_build(uint32_t* table, int which) {
@@ -255,7 +322,7 @@ int launch(sb200_ctx* ctx, Op op, const KArgs& a, cudaStream_t st) {
 #define CASE(O) case O: k_run<O><<<grid, TPB, 0, st>>>(a); break;
     CASE(OP_VERIFY) CASE(OP_VERIFY_DOUBLE) CASE(OP_VERIFY_VARGEN) CASE(OP_SIGN) CASE(OP_SIGN_DOUBLE) CASE(OP_SIGN_VARGEN)
     CASE(OP_KEYGEN) CASE(OP_KEYGEN_DOUBLE) CASE(OP_KEYGEN_VARGEN) CASE(OP_DBG_FQ) CASE(OP_DBG_FR_MUL) CASE(OP_DBG_HADES)
-    CASE(OP_DBG_SMUL)
+    CASE(OP_DBG_SMUL) CASE(OP_DECOMPRESS) CASE(OP_COMPRESS) CASE(OP_FROM_WIDE) CASE(OP_VERIFY_BYTES) CASE(OP_SIGN_BYTES)
 #undef CASE
   }
   ctx->launches.fetch_add(1, std::memory_order_relaxed);
@@ -287,7 +354,7 @@ int run(sb200_ctx* ctx, int64_t n, const Desc& d) {
   // bytes per tuple on the device arena (every array padded to 16 B; bitmap = 4 B per 32 tuples)
   size_t per_tuple = 0;
   for (int k = 0; k < d.nin; k++) per_tuple += (size_t)d.in_words[k] * 4;
-  for (int k = 0; k < d.nout; k++) per_tuple += d.out[k] ? (size_t)d.out_words[k] * 4 : 0;
+  for (int k = 0; k < d.nout; k++) per_tuple += (d.out[k] && d.out_words[k] > 0) ? (size_t)d.out_words[k] * 4 : 0;
 
   const int ndev = (int)ctx->devs.size();
   int64_t per_dev = ((n + ndev - 1) / ndev + 31) & ~(int64_t)31;
@@ -299,7 +366,7 @@ int run(sb200_ctx* ctx, int64_t n, const Desc& d) {
     int slot = 0;
     for (int64_t c0 = lo; c0 < hi; c0 += CHUNK, slot ^= 1) {
       int64_t cn = std::min<int64_t>(CHUNK, hi - c0);
-      size_t need = (size_t)cn * per_tuple + (size_t)((cn + 31) / 32) * 4 + 64 * (MAX_IN + MAX_OUT + 1);
+      size_t need = (size_t)cn * per_tuple + (size_t)((cn + 31) / 32) * 4 * (1 + MAX_OUT) + 64 * (MAX_IN + MAX_OUT + 1);
       if (dc.arena_cap[slot] < need) {
         CU(cudaStreamSynchronize(dc.stream[slot]));
         if (dc.arena[slot]) CU(cudaFree(dc.arena[slot]));
@@ -321,16 +388,19 @@ int run(sb200_ctx* ctx, int64_t n, const Desc& d) {
         a.in[k] = dp;
       }
       uint32_t* dout[MAX_OUT] = {};
+      auto out_bytes = [&](int k) {  // out_words == -1: bitmap-shaped output (one word per 32 tuples)
+        return d.out_words[k] < 0 ? (size_t)((cn + 31) / 32) * 4 : (size_t)cn * d.out_words[k] * 4;
+      };
       for (int k = 0; k < d.nout; k++)
-        if (d.out[k]) a.out[k] = dout[k] = (uint32_t*)carve((size_t)cn * d.out_words[k] * 4);
+        if (d.out[k]) a.out[k] = dout[k] = (uint32_t*)carve(out_bytes(k));
       uint32_t* dbm = nullptr;
       if (d.bitmap) a.bitmap = dbm = (uint32_t*)carve((size_t)((cn + 31) / 32) * 4);
       int rc = launch(ctx, d.op, a, st);
       if (rc) return rc;
       for (int k = 0; k < d.nout; k++)
         if (d.out[k])
-          CU(cudaMemcpyAsync(d.out[k] + (size_t)c0 * d.out_words[k], dout[k], (size_t)cn * d.out_words[k] * 4,
-                             cudaMemcpyDeviceToHost, st));
+          CU(cudaMemcpyAsync(d.out_words[k] < 0 ? d.out[k] + c0 / 32 : d.out[k] + (size_t)c0 * d.out_words[k], dout[k],
+                             out_bytes(k), cudaMemcpyDeviceToHost, st));
       if (d.bitmap)
         CU(cudaMemcpyAsync(d.bitmap + c0 / 32, dbm, (size_t)((cn + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
     }
@@ -481,6 +551,51 @@ int sb200_keygen_vargen(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_
   if (!pk_out) return SB200_ERR_ARG;
   Desc d; d.op = OP_KEYGEN_VARGEN; d.flags = flags; d.nin = 2; d.nout = 1;
   IN(0, sk, 8); IN(1, gen, pt_words(flags)); OUT(0, pk_out, 16);
+  return run(ctx, n, d);
+}
+int sb200_points_decompress(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* bytes, uint32_t* points_out, uint32_t* ok_bitmap) {
+  if (!points_out || !ok_bitmap || (flags & SB200_POINTS_AFFINE)) return SB200_ERR_ARG;
+  Desc d; d.op = OP_DECOMPRESS; d.flags = flags; d.nin = 1; d.nout = 1; d.bitmap = ok_bitmap;
+  IN(0, (const uint32_t*)bytes, 8); OUT(0, points_out, 16);
+  return run(ctx, n, d);
+}
+int sb200_points_compress(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* points, uint8_t* bytes_out) {
+  if (!bytes_out) return SB200_ERR_ARG;
+  Desc d; d.op = OP_COMPRESS; d.flags = flags; d.nin = 1; d.nout = 1;
+  IN(0, points, pt_words(flags)); OUT(0, (uint32_t*)bytes_out, 8);
+  return run(ctx, n, d);
+}
+int sb200_scalars_from_wide(sb200_ctx* ctx, int64_t n, uint32_t flags, int field, const uint8_t* wide, uint32_t* out) {
+  if (!out || field < 0 || field > 1 || (flags & SB200_POINTS_AFFINE)) return SB200_ERR_ARG;
+  Desc d; d.op = OP_FROM_WIDE; d.flags = flags; d.aux = field; d.nin = 1; d.nout = 1;
+  IN(0, (const uint32_t*)wide, 16); OUT(0, out, 8);
+  return run(ctx, n, d);
+}
+int sb200_fq_to_mont(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* in, uint32_t* out) {
+  if (!out || (flags & SB200_POINTS_AFFINE)) return SB200_ERR_ARG;
+  Desc d; d.op = OP_DBG_FQ; d.flags = flags; d.aux = 5; d.nin = 2; d.nout = 1;
+  IN(0, in, 8); IN(1, nullptr, 0); OUT(0, out, 8);
+  return run(ctx, n, d);
+}
+int sb200_fq_from_mont(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* in, uint32_t* out) {
+  if (!out || (flags & SB200_POINTS_AFFINE)) return SB200_ERR_ARG;
+  Desc d; d.op = OP_DBG_FQ; d.flags = flags; d.aux = 6; d.nin = 2; d.nout = 1;
+  IN(0, in, 8); IN(1, nullptr, 0); OUT(0, out, 8);
+  return run(ctx, n, d);
+}
+int sb200_verify_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg,
+                       uint32_t* verdicts, uint32_t* invalid) {
+  if (!verdicts || (flags & SB200_POINTS_AFFINE)) return SB200_ERR_ARG;
+  Desc d; d.op = OP_VERIFY_BYTES; d.flags = flags | SB200_POINTS_AFFINE; d.nin = 3; d.nout = 1; d.bitmap = verdicts;
+  IN(0, (const uint32_t*)pk, 8); IN(1, (const uint32_t*)sig, 16); IN(2, (const uint32_t*)msg, 8);
+  d.out[0] = invalid; d.out_words[0] = -1;  // bitmap-shaped output: one word per 32 tuples
+  return run(ctx, n, d);
+}
+int sb200_sign_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* sk, const uint8_t* msg, const uint8_t* nonce,
+                     uint8_t* sig_out) {
+  if (!sig_out || (flags & SB200_POINTS_AFFINE)) return SB200_ERR_ARG;
+  Desc d; d.op = OP_SIGN_BYTES; d.flags = flags; d.nin = 3; d.nout = 1;
+  IN(0, (const uint32_t*)sk, 8); IN(1, (const uint32_t*)msg, 8); IN(2, (const uint32_t*)nonce, 8); OUT(0, (uint32_t*)sig_out, 16);
   return run(ctx, n, d);
 }
 int sb200_dbg_fq(sb200_ctx* ctx, int64_t n, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {

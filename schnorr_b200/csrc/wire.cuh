@@ -1,0 +1,166 @@
+// Wire formats on the device: the reference's serialised forms are accepted / produced
+// directly, so a caller holding bytes never decodes on the host.
+//
+//   JubJubAffine::to_bytes / from_bytes   (32 B: v little-endian, bit 255 = low bit of u; no subgroup check)
+//       as used by Signature::{to,from}_bytes   /root/reference/src/signatures.rs:106-123
+//       and PublicKey::{to,from}_bytes          /root/reference/src/keys/public.rs:87-101
+//   JubJubScalar::from_bytes              (32 B canonical, rejects >= r)     /root/reference/src/keys/secret.rs:96-102
+//   BlsScalar::from_bytes                 (32 B canonical, rejects >= q)
+//   Field::random = from_bytes_wide       (64 B little-endian reduced mod r / mod q)  /root/reference/src/keys/secret.rs:83,155
+#pragma once
+#include "core.cuh"
+
+namespace sb200 {
+
+SB_HD bool lt_q(const uint32_t* k) {
+  uint32_t t[8];
+  const uint32_t qq[8] = SB200_FQ_MOD_INIT;
+  return sub8(t, k, qq) != 0;
+}
+
+// x^e for a constant little-endian exponent of `bits` bits, 4-bit fixed windows
+SB_HD fq fq_pow_const(const fq& x, const uint32_t* e, int bits) {
+  fq tab[16];
+  tab[0] = fq_one();
+  tab[1] = x;
+#pragma unroll 1
+  for (int i = 2; i < 16; i++) tab[i] = fq_mul(tab[i - 1], x);
+  fq acc = fq_one();
+#pragma unroll 1
+  for (int w = (bits + 3) / 4 - 1; w >= 0; w--) {
+    acc = fq_sqr(fq_sqr(fq_sqr(fq_sqr(acc))));
+    acc = fq_mul(acc, tab[(e[w >> 3] >> ((w & 7) * 4)) & 15u]);
+  }
+  return acc;
+}
+
+// Tonelli-Shanks square root in F_q (2-adicity 32).  Returns false if x is a non-residue.  Variable time
+// (inputs are public: keys and signatures).
+SB_HD bool fq_sqrt(const fq& x, fq& root) {
+  const uint32_t e[8] = SB200_FQ_SQRT_EXP_INIT;
+  const fq g = {SB200_FQ_ROOT_OF_UNITY_INIT};
+  const fq one = fq_one();
+  fq w = fq_pow_const(x, e, SB200_FQ_SQRT_EXP_BITS);  // x^((t-1)/2)
+  fq a = fq_mul(x, w);                                 // x^((t+1)/2)
+  fq b = fq_mul(a, w);                                 // x^t, in the 2^32-order subgroup
+  fq z = g;
+  int v = 32;
+  bool ok = true;
+  if (fq_is_zero(x)) {
+    root = x;
+    return true;
+  }
+#pragma unroll 1
+  while (!fq_eq(b, one)) {
+    int k = 0;
+    fq tmp = b;
+#pragma unroll 1
+    while (!fq_eq(tmp, one) && k < v) {
+      tmp = fq_sqr(tmp);
+      k++;
+    }
+    if (k >= v) {  // order of b does not divide 2^(v-1): non-residue
+      ok = false;
+      break;
+    }
+    fq ww = z;
+#pragma unroll 1
+    for (int i = 0; i < v - k - 1; i++) ww = fq_sqr(ww);
+    a = fq_mul(a, ww);
+    z = fq_sqr(ww);
+    b = fq_mul(b, z);
+    v = k;
+  }
+  root = a;
+  return ok;
+}
+
+// 32 bytes (as 8 LE words) -> affine point, Montgomery.  false <=> the reference's from_bytes returns None.
+SB_HD bool point_decompress(const uint32_t* in, fq& u, fq& v) {
+  uint32_t vb[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) vb[i] = in[i];
+  uint32_t sign = vb[7] >> 31;
+  vb[7] &= 0x7fffffffu;
+  bool ok = lt_q(vb);
+  fq vc;
+#pragma unroll
+  for (int i = 0; i < 8; i++) vc.v[i] = ok ? vb[i] : 0u;
+  v = fq_to_mont(vc);
+  fq v2 = fq_sqr(v);
+  fq num = fq_sub(v2, fq_one());
+  fq den = fq_add(fq_one(), fq_mul(ed_d(), v2));
+  fq x = fq_mul(num, fq_inv(den));  // den = 0 -> inverse "0" -> x = 0, as invert().unwrap_or(zero)
+  ok &= fq_sqrt(x, u);
+  uint32_t parity = fq_from_mont(u).v[0] & 1u;
+  u = fq_select(u, fq_neg(u), parity != sign);
+  return ok;
+}
+
+// affine (u, v), Montgomery -> 32 bytes
+SB_HD void point_compress(const fq& u, const fq& v, uint32_t* out) {
+  fq vc = fq_from_mont(v);
+  uint32_t parity = fq_from_mont(u).v[0] & 1u;
+#pragma unroll
+  for (int i = 0; i < 8; i++) out[i] = vc.v[i];
+  out[7] |= parity << 31;
+}
+
+// 512-bit little-endian integer (16 words) reduced mod r -> canonical scalar.
+// lo mod r = mont(mont(lo, R^2), 1);  hi * 2^256 mod r = mont(hi, R^2);  (mont(a, b) needs only b < r)
+SB_HD void fr_from_wide(const uint32_t* w, uint32_t* out) {
+  fr lo, hi, one, r2 = {SB200_FR_R2_INIT};
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    lo.v[i] = w[i];
+    hi.v[i] = w[8 + i];
+    one.v[i] = i == 0 ? 1u : 0u;
+  }
+  fr a = fr_mont_mul(fr_mont_mul(lo, r2), one);
+  fr b = fr_mont_mul(hi, r2);
+  fr s;
+  add8(s.v, a.v, b.v);  // < 2r < 2^256
+  cond_sub_p<FrP>(s.v);
+#pragma unroll
+  for (int i = 0; i < 8; i++) out[i] = s.v[i];
+}
+// same mod q, result in Montgomery form (what BlsScalar holds):  lo*R + hi*R^2 = mont(lo, R^2) + mont(mont(hi, R^2), R^2)
+SB_HD fq fq_from_wide(const uint32_t* w) {
+  fq lo, hi;
+  const fq r2 = {SB200_FQ_R2_INIT};
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    lo.v[i] = w[i];
+    hi.v[i] = w[8 + i];
+  }
+  // reduce the raw halves below q first (they may be >= q: up to 2 subtractions since 2^256 < 3q)
+  cond_sub_p<FqP>(lo.v); cond_sub_p<FqP>(lo.v);
+  cond_sub_p<FqP>(hi.v); cond_sub_p<FqP>(hi.v);
+  return fq_add(fq_mul(lo, r2), fq_mul(fq_mul(hi, r2), r2));
+}
+
+// PublicKey::from_bytes + Signature::from_bytes + BlsScalar::from_bytes + verify, one tuple.
+// `invalid` <=> any from_bytes of the reference would fail (InvalidData); then the verdict is false.
+SB_HD bool verify_bytes_core(const uint32_t* pk32, const uint32_t* sig64, const uint32_t* msg32, const uint32_t* combG,
+                             bool& invalid) {
+  point_in PK, R;
+  PK.affine = R.affine = true;
+  PK.Z = R.Z = fq_one();
+  bool ok = point_decompress(pk32, PK.U, PK.V);
+  ok &= point_decompress(sig64 + 8, R.U, R.V);
+  uint32_t u[8], mb[8], c[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    u[i] = sig64[i];
+    mb[i] = msg32[i];
+  }
+  ok &= scalar_lt_r(u) & lt_q(mb);
+  fq mc;
+#pragma unroll
+  for (int i = 0; i < 8; i++) mc.v[i] = ok ? mb[i] : 0u;
+  invalid = !ok;
+  bool verdict = verify_core(PK, u, R, fq_to_mont(mc), combG, c);
+  return ok & verdict;
+}
+
+}  // namespace sb200

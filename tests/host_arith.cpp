@@ -3,7 +3,7 @@
 // Test scaffolding: never linked into libschnorr_b200.so.
 #include <cstring>
 #include <vector>
-#include "../schnorr_b200/csrc/core.cuh"
+#include "../schnorr_b200/csrc/wire.cuh"
 using namespace sb200;
 
 static fq L(const uint32_t* p) { fq r; memcpy(r.v, p, 32); return r; }
@@ -56,6 +56,14 @@ void h_sign_double(const uint32_t* sk, const uint32_t* nonce, const uint32_t* m,
 }
 void h_sign_vargen(const uint32_t* sk, const uint32_t* gen, int affine, const uint32_t* nonce, const uint32_t* m, uint32_t* u, uint32_t* Ruv, uint32_t* c) {
   fq a, b; sign_vargen_core(sk, P(gen, affine), nonce, L(m), u, a, b, c); S(Ruv, a); S(Ruv + 8, b);
+}
+int h_decompress(const uint32_t* b, uint32_t* uv) { fq u, v; bool ok = point_decompress(b, u, v); S(uv, u); S(uv + 8, v); return ok; }
+void h_compress(const uint32_t* uv, uint32_t* b) { point_compress(L(uv), L(uv + 8), b); }
+void h_fr_from_wide(const uint32_t* w, uint32_t* r) { fr_from_wide(w, r); }
+void h_fq_from_wide(const uint32_t* w, uint32_t* r) { S(r, fq_from_wide(w)); }
+int h_fq_sqrt(const uint32_t* a, uint32_t* r) { fq x; bool ok = fq_sqrt(L(a), x); S(r, x); return ok; }
+int h_verify_bytes(const uint32_t* pk, const uint32_t* sig, const uint32_t* msg, const uint32_t* combG, int* invalid) {
+  bool inv; bool ok = verify_bytes_core(pk, sig, msg, combG, inv); *invalid = inv; return ok;
 }
 void h_fixed_mul(const uint32_t* comb, const uint32_t* k, uint32_t* uv) {
   fq a, b; ext_to_affine(fixed_base_mul(comb, k), a, b); S(uv, a); S(uv + 8, b);

@@ -248,3 +248,72 @@ def test_empty_batch(engine):
     ok, c = engine.verify(np.zeros((0, 16), np.uint32), np.zeros((0, 8), np.uint32), np.zeros((0, 16), np.uint32),
                           np.zeros((0, 8), np.uint32))
     assert ok.size == 0
+
+
+# ---- wire formats on the device ---------------------------------------------------
+def test_points_compress_decompress(engine):
+    rnd = random.Random(30)
+    pts = V.torsion_points() + [o.G, o.G_NUMS] + [V.rand_curve_point(rnd) for _ in range(120)]
+    enc = b"".join(o.affine_to_bytes(p) for p in pts)
+    got, ok = engine.points_decompress(enc)
+    assert ok.all() and V.points_out(got) == pts
+    assert engine.points_compress(V.points(pts)).tobytes() == enc
+    zs = [rnd.randrange(1, Q) for _ in pts]
+    assert engine.points_compress(V.points(pts, zs), affine=False).tobytes() == enc
+    # what JubJubAffine::from_bytes rejects: non-canonical v, v not on the curve
+    raw = [v.to_bytes(32, "little") for v in list(range(2, 200)) + [Q, Q + 1, (1 << 255) - 1]]
+    exp = [o.affine_from_bytes(b) for b in raw]
+    got, ok = engine.points_decompress(b"".join(raw))
+    assert list(ok) == [e is not None for e in exp]
+    assert [p for p, k in zip(V.points_out(got), ok) if k] == [e for e in exp if e is not None]
+    assert not all(ok) and any(ok)
+    # sign bit selects the root
+    flipped = bytearray(o.affine_to_bytes(o.G)); flipped[31] ^= 0x80
+    got, ok = engine.points_decompress(bytes(flipped))
+    assert ok[0] and V.points_out(got)[0] == o.pt_neg(o.G)
+
+
+def test_from_bytes_wide(engine):
+    rnd = random.Random(31)
+    ws = [0, 1, R, Q, (1 << 512) - 1, (1 << 256) - 1, 1 << 256, R << 256, Q << 200] + [rnd.randrange(1 << 512) for _ in range(300)]
+    data = b"".join(w.to_bytes(64, "little") for w in ws)
+    assert V.ints_out(engine.scalars_from_wide(data, 0)) == [w % R for w in ws]
+    assert [V.unmont(r) for r in engine.scalars_from_wide(data, 1)] == [w % Q for w in ws]
+    # = the draws of the reference's RNG: nonce i of a StdRng used only for signing
+    rng = o.StdRng.seed_from_u64(2321)
+    blocks = b"".join(o.chacha_block(rng.key, i) for i in range(8))
+    assert V.ints_out(engine.scalars_from_wide(blocks, 0)) == [o.nonce_from_block(rng.key, i) for i in range(8)]
+    xs = [rnd.randrange(Q) for _ in range(50)]
+    assert V.ints_out(engine.fq_to_mont(V.scalars(xs))) == [x * V.RADIX % Q for x in xs]
+    assert V.ints_out(engine.fq_from_mont(V.fqs(xs))) == xs
+
+
+def test_sign_and_verify_bytes(engine):
+    rnd = random.Random(32)
+    n = 150
+    sk, nonce, m = make_single(rnd, n)
+    sigs = engine.sign_bytes(b"".join(x.to_bytes(32, "little") for x in sk), b"".join(x.to_bytes(32, "little") for x in m),
+                             b"".join(x.to_bytes(32, "little") for x in nonce))
+    exp = [o.sign(a, b, mm, mul=V.mul) for a, b, mm in zip(sk, nonce, m)]
+    assert [bytes(s) for s in sigs] == [e[0].to_bytes(32, "little") + o.affine_to_bytes(e[1]) for e in exp]  # Signature::to_bytes
+    pk = [o.affine_to_bytes(V.mul(o.G, a)) for a in sk]
+    sig = [bytearray(s) for s in sigs]
+    msg = [bytearray(x.to_bytes(32, "little")) for x in m]
+    want_ok, want_inv = [True] * n, [False] * n
+    for i in range(n):
+        k = i % 8
+        if k == 1:   # corrupted u (still canonical)
+            sig[i][0] ^= 1; want_ok[i] = False
+        elif k == 2:  # u >= r: JubJubScalar::from_bytes fails
+            sig[i][:32] = (exp[i][0] + R).to_bytes(32, "little"); want_ok[i] = False; want_inv[i] = True
+        elif k == 3:  # R bytes not on the curve
+            bad = next(v for v in range(2 + i, 400) if o.affine_from_bytes(v.to_bytes(32, "little")) is None)
+            sig[i][32:] = bad.to_bytes(32, "little"); want_ok[i] = False; want_inv[i] = True
+        elif k == 4:  # message >= q
+            msg[i][:] = (Q + i).to_bytes(32, "little"); want_ok[i] = False; want_inv[i] = True
+        elif k == 5:  # someone else's key
+            pk[i] = pk[(i + 1) % n]; want_ok[i] = False
+        elif k == 6:  # pk bytes with non-canonical v
+            pk[i] = (Q + 3).to_bytes(32, "little"); want_ok[i] = False; want_inv[i] = True
+    ok, inv = engine.verify_bytes(b"".join(pk), b"".join(bytes(s) for s in sig), b"".join(bytes(x) for x in msg))
+    assert list(ok) == want_ok and list(inv) == want_inv

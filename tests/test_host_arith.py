@@ -1,6 +1,7 @@
 """The CUDA headers compiled for the CPU (carry-chain blocks emulated): every per-tuple routine the kernels
 run, against the oracle.  Catches logic errors without a GPU; the GPU parity tests then only have to
 catch PTX-level ones."""
+import ctypes
 import random
 
 import numpy as np
@@ -113,3 +114,48 @@ def test_sign_verify_all_variants(lib, tabs):
         assert lib.h_verify_vargen(H.ptr(H.pt_mont(pkv)), H.ptr(H.pt_mont(gen)), H.ptr(H.limbs(eu)), H.ptr(H.pt_mont(eR)), H.ptr(H.mont(m)), 1, H.ptr(c)) == 1
         assert lib.h_verify_vargen(H.ptr(H.pt_mont(pkv, z1)), H.ptr(H.pt_mont(gen, z2)), H.ptr(H.limbs(eu)), H.ptr(H.pt_mont(eR, z1)), H.ptr(H.mont(m)), 0, H.ptr(c)) == 1
         assert lib.h_verify_vargen(H.ptr(H.pt_mont(pkv)), H.ptr(H.pt_mont(o.G)), H.ptr(H.limbs(eu)), H.ptr(H.pt_mont(eR)), H.ptr(H.mont(m)), 1, H.ptr(c)) == 0
+
+
+def test_wire_formats(lib, tabs):
+    """device-side JubJubAffine::{to,from}_bytes, from_bytes_wide and the byte-level verify, on the CPU build"""
+    rnd = random.Random(8)
+    out, uv, b32 = np.zeros(8, np.uint32), np.zeros(16, np.uint32), np.zeros(8, np.uint32)
+    # sqrt: residues and non-residues, 0, 1, values whose x^t has maximal 2-power order
+    for x in [0, 1, 4, Q - 1, 5, 7] + [rnd.randrange(Q) for _ in range(30)]:
+        ok = lib.h_fq_sqrt(H.ptr(H.mont(x)), H.ptr(out))
+        is_sq = x == 0 or pow(x, (Q - 1) // 2, Q) == 1
+        assert bool(ok) == is_sq
+        if is_sq:
+            assert pow(H.unmont(out), 2, Q) == x
+    # decompress / compress
+    pts = V.torsion_points() + [o.G, o.G_NUMS] + [V.rand_curve_point(rnd) for _ in range(10)]
+    for P in pts:
+        enc = o.affine_to_bytes(P)
+        assert lib.h_decompress(H.ptr(np.frombuffer(enc, np.uint32).copy()), H.ptr(uv)) == 1
+        assert (H.unmont(uv[:8]), H.unmont(uv[8:])) == P
+        lib.h_compress(H.ptr(H.pt_mont(P)), H.ptr(b32))
+        assert b32.tobytes() == enc
+    for v in list(range(2, 40)) + [Q, Q + 1, (1 << 255) - 1]:
+        enc = v.to_bytes(32, "little")
+        exp = o.affine_from_bytes(enc)
+        got = lib.h_decompress(H.ptr(np.frombuffer(enc, np.uint32).copy()), H.ptr(uv))
+        assert bool(got) == (exp is not None)
+        if exp is not None:
+            assert (H.unmont(uv[:8]), H.unmont(uv[8:])) == exp
+    # from_bytes_wide
+    for w in [0, 1, R, Q, (1 << 512) - 1, (1 << 256) - 1, 1 << 256, R << 256] + [rnd.randrange(1 << 512) for _ in range(40)]:
+        wb = np.frombuffer(w.to_bytes(64, "little"), np.uint32).copy()
+        lib.h_fr_from_wide(H.ptr(wb), H.ptr(out)); assert H.to_int(out) == w % R
+        lib.h_fq_from_wide(H.ptr(wb), H.ptr(out)); assert H.unmont(out) == w % Q
+    # byte-level verify
+    sk, nonce, m = rnd.randrange(R), rnd.randrange(R), rnd.randrange(Q)
+    u, Rp, _ = o.sign(sk, nonce, m, mul=V.mul)
+    pkb = o.affine_to_bytes(V.mul(o.G, sk))
+    sig = u.to_bytes(32, "little") + o.affine_to_bytes(Rp)
+    inv = ctypes.c_int(0)
+    B = lambda b: H.ptr(np.frombuffer(b, np.uint32).copy())
+    assert lib.h_verify_bytes(B(pkb), B(sig), B(m.to_bytes(32, "little")), H.ptr(tabs[0]), ctypes.byref(inv)) == 1 and inv.value == 0
+    assert lib.h_verify_bytes(B(pkb), B(sig), B(((m + 1) % Q).to_bytes(32, "little")), H.ptr(tabs[0]), ctypes.byref(inv)) == 0 and inv.value == 0
+    assert lib.h_verify_bytes(B(pkb), B(sig), B(Q.to_bytes(32, "little")), H.ptr(tabs[0]), ctypes.byref(inv)) == 0 and inv.value == 1
+    bad_sig = (u + R).to_bytes(32, "little") + o.affine_to_bytes(Rp)
+    assert lib.h_verify_bytes(B(pkb), B(bad_sig), B(m.to_bytes(32, "little")), H.ptr(tabs[0]), ctypes.byref(inv)) == 0 and inv.value == 1

@@ -233,6 +233,17 @@ def main():
     w("#define SB200_G_V_INIT %s" % fmt(mont(G[1])))
     w("#define SB200_GP_U_INIT %s" % fmt(mont(GP[0])))
     w("#define SB200_GP_V_INIT %s" % fmt(mont(GP[1])))
+    # Tonelli-Shanks data for F_q (q - 1 = 2^32 * t, t odd): 2^32-th primitive root g = 7^t (7 is a generator,
+    # as in dusk-bls12_381's ROOT_OF_UNITY derivation; any primitive root gives the same decompressed point
+    # because the sign bit picks the root) and the exponent (t - 1) / 2.
+    t_odd = (Q - 1) >> 32
+    assert t_odd & 1 and pow(7, (Q - 1) // 2, Q) == Q - 1
+    g_root = pow(7, t_odd, Q)
+    assert pow(g_root, 1 << 31, Q) == Q - 1
+    w("// Tonelli-Shanks in F_q: 2-adicity 32, g = 7^t primitive 2^32-th root of unity, e = (t-1)/2")
+    w("#define SB200_FQ_ROOT_OF_UNITY_INIT %s" % fmt(mont(g_root)))
+    w("#define SB200_FQ_SQRT_EXP_INIT %s   // (t - 1) / 2, plain integer" % fmt((t_odd - 1) // 2))
+    w("#define SB200_FQ_SQRT_EXP_BITS %d" % ((t_odd - 1) // 2).bit_length())
     w("// Hades252: WIDTH 5, 8 full + 59 partial rounds; round keys = SHA-512 chain over \"poseidon-for-plonk\"")
     w("// (dusk-hades ark.bin), first 335 of 960; MDS[i][j] = 1/(i + j + 5) (dusk-hades mds.bin).")
     w("#define SB200_HADES_NRC %d" % ((FULL + PARTIAL) * WIDTH))
