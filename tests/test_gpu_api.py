@@ -220,3 +220,37 @@ def test_multi_device_context_shards_without_collective():
     ok, _ = e.verify(pk, u, R_, msg)
     assert ok.tolist() == [(i % 3) != 0 for i in range(n)]
     e.close()
+
+
+def test_cpp_api_mirror_runs_reference_tests():
+    """include/schnorr_b200.hpp (the C++ host layer above the C ABI) re-runs the reference's tests on the GPU;
+    its seeded outputs must equal the oracle's bytes."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "build", "test_api_cpp")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(root, "tests", "cpp", "test_api.cpp"),
+                           "-L" + os.path.join(root, "schnorr_b200"), "-lschnorr_b200",
+                           "-Wl,-rpath," + os.path.join(root, "schnorr_b200")])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "ALL OK" in out.stdout
+    kv = dict(l.split("=", 1) for l in out.stdout.splitlines() if "=" in l)
+    rng = o.StdRng.seed_from_u64(2321)
+    sk, m = rng.random_fr(), rng.random_fq()
+    u, Rp, _ = o.sign(sk, rng.random_fr(), m, mul=V.mul)
+    assert kv["sk"] == sk.to_bytes(32, "little").hex() and kv["msg"] == m.to_bytes(32, "little").hex()
+    assert kv["pk"] == o.affine_to_bytes(V.mul(o.G, sk)).hex()
+    assert kv["sig"] == (u.to_bytes(32, "little") + o.affine_to_bytes(Rp)).hex()
+    rng = o.StdRng.seed_from_u64(2321)
+    sk, m = rng.random_fr(), rng.random_fq()
+    u, Rp, Rpp, _ = o.sign_double(sk, rng.random_fr(), m, mul=V.mul)
+    assert kv["sig_double"] == (u.to_bytes(32, "little") + o.affine_to_bytes(Rp) + o.affine_to_bytes(Rpp)).hex()
+    rng = o.StdRng.seed_from_u64(2321)
+    sk, s = rng.random_fr(), rng.random_fr()
+    gen = V.mul(o.G, s)
+    m = rng.random_fq()
+    u, Rp, _ = o.sign_vargen(sk, gen, rng.random_fr(), m, mul=V.mul)
+    assert kv["vargen_generator"] == o.affine_to_bytes(gen).hex()
+    assert kv["sig_vargen"] == (u.to_bytes(32, "little") + o.affine_to_bytes(Rp)).hex()

@@ -35,3 +35,22 @@ timeit("verify_double", lambda: e.call("verify_double", n, fl, P(pk), P(pk2), P(
 timeit("sign", lambda: e.call("sign", n, fl, P(u), P(m), P(u), P(uo), P(Ro), P(co)))
 timeit("sign_double", lambda: e.call("sign_double", n, fl, P(u), P(m), P(u), P(uo), P(Ro), P(Ro2), P(co)))
 timeit("keygen", lambda: e.call("keygen", n, fl, P(u), P(Ro)))
+
+# byte-level entry points (valid inputs needed: decompression must succeed)
+nb = min(n, 1 << 18)
+sk_np = rnd_fq(nb, 8); sk_np[:, 7] &= 0x07FFFFFF
+msg_np = rnd_fq(nb, 8)
+sigb = e.sign_bytes(sk_np.view(np.uint8), msg_np.view(np.uint8), sk_np.view(np.uint8))
+pkb = e.points_compress(e.keygen(sk_np))
+tb = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).to(dev)
+d_pkb, d_sigb, d_msgb, d_skb = tb(pkb), tb(sigb), tb(msg_np), tb(sk_np)
+d_sigo = torch.empty((nb, 16), dtype=torch.int32, device=dev)
+d_pts = torch.empty((nb, 16), dtype=torch.int32, device=dev)
+bm2 = torch.zeros((nb + 31) // 32, dtype=torch.int32, device=dev)
+n_save, n = n, nb
+timeit("verify_bytes", lambda: e.call("verify_bytes", nb, DEVICE_PTRS, P(d_pkb), P(d_sigb), P(d_msgb), P(bm2), None))
+import numpy as _np
+assert _np.unpackbits(bm2.cpu().numpy().view(_np.uint8), bitorder="little")[:nb].all(), "byte-level verify of valid signatures"
+timeit("sign_bytes", lambda: e.call("sign_bytes", nb, DEVICE_PTRS, P(d_skb), P(d_msgb), P(d_skb), P(d_sigo)))
+timeit("decompress", lambda: e.call("points_decompress", nb, DEVICE_PTRS, P(d_pkb), P(d_pts), P(bm2)))
+timeit("compress", lambda: e.call("points_compress", nb, fl, P(d_pts), P(d_pkb)))
