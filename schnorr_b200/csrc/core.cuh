@@ -130,6 +130,26 @@ SB_HD void ext_to_affine(const ext& p, fq& u, fq& v) {
   v = fq_mul(p.Y, zi);
 }
 
+// Montgomery's trick: z[0..n) <- 1/z[0..n) with ONE inversion and 3(n-1) multiplications (all z[j] != 0:
+// Z coordinates of complete-addition results).  Used to convert several points per thread to affine.
+SB_HD void batch_inverse(fq* z, fq* pre, int n) {
+  fq acc = z[0];
+  pre[0] = fq_one();
+#pragma unroll 1
+  for (int j = 1; j < n; j++) {
+    pre[j] = acc;
+    acc = fq_mul(acc, z[j]);
+  }
+  fq inv = fq_inv(acc);
+#pragma unroll 1
+  for (int j = n - 1; j > 0; j--) {
+    fq zj = z[j];
+    z[j] = fq_mul(inv, pre[j]);
+    inv = fq_mul(inv, zj);
+  }
+  z[0] = inv;
+}
+
 // u = nonce - c * sk  (mod r)
 SB_HD void sign_finish(const uint32_t* nonce, const uint32_t* c, const uint32_t* sk, uint32_t* u_out) {
   fr a, b, n;

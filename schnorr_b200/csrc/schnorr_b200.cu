@@ -263,6 +263,73 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
   }
 }
 
+// Fixed-base signing / key generation with several tuples per thread: the scalar multiples of G (and G') are
+// computed first, all their Z coordinates are inverted together (one field inversion per thread instead of one
+// per point: the inversion is a third of a single signature's work), then each tuple is finished.
+// Thread t of a CTA handles tuples base + j * TPB + t (j < K): loads and stores stay coalesced.
+constexpr int SIGN_K = 4;
+template <int OP>
+__global__ void __launch_bounds__(TPB, 4) k_fixed_batch(const KArgs a) {
+  constexpr bool DOUBLE = (OP == OP_SIGN_DOUBLE || OP == OP_KEYGEN_DOUBLE);
+  constexpr bool SIGN = (OP == OP_SIGN || OP == OP_SIGN_DOUBLE || OP == OP_SIGN_BYTES);
+  constexpr int NP = DOUBLE ? 2 * SIGN_K : SIGN_K;
+  const int64_t base = (int64_t)blockIdx.x * TPB * SIGN_K + threadIdx.x;
+  fq X[NP], Y[NP], Z[NP], pre[NP];
+  // scalar whose multiple is needed: the nonce when signing, the secret key for keygen
+  const uint32_t* kin = SIGN ? a.in[2] : a.in[0];
+#pragma unroll 1
+  for (int j = 0; j < SIGN_K; j++) {
+    int64_t i = base + (int64_t)j * TPB;
+    if (i >= a.n) i = a.n - 1;
+    uint32_t k[8];
+    ldg_scalar(kin + i * 8, k);
+    ext p = fixed_base_mul(a.combG, k);
+    X[j] = p.X; Y[j] = p.Y; Z[j] = p.Z;
+    if (DOUBLE) {
+      ext q = fixed_base_mul(a.combGp, k);
+      X[SIGN_K + j] = q.X; Y[SIGN_K + j] = q.Y; Z[SIGN_K + j] = q.Z;
+    }
+  }
+  batch_inverse(Z, pre, NP);
+#pragma unroll 1
+  for (int j = 0; j < SIGN_K; j++) {
+    int64_t i = base + (int64_t)j * TPB;
+    const bool active = i < a.n;
+    if (!active) i = a.n - 1;
+    fq Ru = fq_mul(X[j], Z[j]), Rv = fq_mul(Y[j], Z[j]), Rpu, Rpv;
+    if (DOUBLE) {
+      Rpu = fq_mul(X[SIGN_K + j], Z[SIGN_K + j]);
+      Rpv = fq_mul(Y[SIGN_K + j], Z[SIGN_K + j]);
+    }
+    if (!SIGN) {
+      if (active) {
+        stg_point(a.out[0], i, Ru, Rv);
+        if (DOUBLE) stg_point(a.out[1], i, Rpu, Rpv);
+      }
+      continue;
+    }
+    uint32_t sk[8], nonce[8], u[8], c[8];
+    ldg_scalar(a.in[0] + i * 8, sk);
+    ldg_scalar(a.in[2] + i * 8, nonce);
+    fq m = ldg_fq(a.in[1] + i * 8);
+    if (OP == OP_SIGN_BYTES) m = fq_to_mont(m);
+    if (DOUBLE) challenge5(Ru, Rv, Rpu, Rpv, m, c); else challenge3(Ru, Rv, m, c);
+    sign_finish(nonce, c, sk, u);
+    if (!active) continue;
+    if (OP == OP_SIGN_BYTES) {
+      uint32_t rb[8];
+      point_compress(Ru, Rv, rb);
+      stg8(a.out[0] + i * 16, u);
+      stg8(a.out[0] + i * 16 + 8, rb);
+    } else {
+      stg8(a.out[0] + i * 8, u);
+      stg_point(a.out[1], i, Ru, Rv);
+      if (DOUBLE) stg_point(a.out[2], i, Rpu, Rpv);
+      if (a.out[3]) stg8(a.out[3] + i * 8, c);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(TPB) k_comb_build(uint32_t* table, int which) {
   int t = blockIdx.x * TPB + threadIdx.x;
   if (t >= COMB_WINDOWS * COMB_ENTRIES) return;  // 524 304 entries at 16-bit windows
@@ -318,11 +385,15 @@ namespace {
 int launch(sb200_ctx* ctx, Op op, const KArgs& a, cudaStream_t st) {
   if (a.n <= 0) return SB200_OK;
   unsigned grid = (unsigned)((a.n + TPB - 1) / TPB);
+  unsigned gridk = (unsigned)((a.n + TPB * SIGN_K - 1) / (TPB * SIGN_K));
   switch (op) {
+#define CASEK(O) case O: k_fixed_batch<O><<<gridk, TPB, 0, st>>>(a); break;
+    CASEK(OP_SIGN) CASEK(OP_SIGN_DOUBLE) CASEK(OP_KEYGEN) CASEK(OP_KEYGEN_DOUBLE) CASEK(OP_SIGN_BYTES)
+#undef CASEK
 #define CASE(O) case O: k_run<O><<<grid, TPB, 0, st>>>(a); break;
-    CASE(OP_VERIFY) CASE(OP_VERIFY_DOUBLE) CASE(OP_VERIFY_VARGEN) CASE(OP_SIGN) CASE(OP_SIGN_DOUBLE) CASE(OP_SIGN_VARGEN)
-    CASE(OP_KEYGEN) CASE(OP_KEYGEN_DOUBLE) CASE(OP_KEYGEN_VARGEN) CASE(OP_DBG_FQ) CASE(OP_DBG_FR_MUL) CASE(OP_DBG_HADES)
-    CASE(OP_DBG_SMUL) CASE(OP_DECOMPRESS) CASE(OP_COMPRESS) CASE(OP_FROM_WIDE) CASE(OP_VERIFY_BYTES) CASE(OP_SIGN_BYTES)
+    CASE(OP_VERIFY) CASE(OP_VERIFY_DOUBLE) CASE(OP_VERIFY_VARGEN) CASE(OP_SIGN_VARGEN)
+    CASE(OP_KEYGEN_VARGEN) CASE(OP_DBG_FQ) CASE(OP_DBG_FR_MUL) CASE(OP_DBG_HADES)
+    CASE(OP_DBG_SMUL) CASE(OP_DECOMPRESS) CASE(OP_COMPRESS) CASE(OP_FROM_WIDE) CASE(OP_VERIFY_BYTES)
 #undef CASE
   }
   ctx->launches.fetch_add(1, std::memory_order_relaxed);
