@@ -551,8 +551,18 @@ SB_HD fq fq_select(const fq& a, const fq& b, bool take_b) {
 
 // Montgomery product a * b * 2^-256 mod q, inputs and output canonical (< q).
 // 8 rows x (8 + 6) wide products.
+SB_HD void mul_wide16(uint32_t* T, const uint32_t* a, const uint32_t* b);
+SB_HD fq mont_reduce16(const uint32_t* t);
+#ifndef SB_MUL_SEPARATED
+#define SB_MUL_SEPARATED 0  // experiment: schoolbook product (64) + separated reduction (48) instead of the interleaved 120
+#endif
 SB_HD fq fq_mul_inl(const fq& a, const fq& b) {
   SB_COUNT(fq_mul, 1);
+#if SB_MUL_SEPARATED
+  uint32_t T[16];
+  mul_wide16(T, a.v, b.v);
+  return mont_reduce16(T);
+#endif
   uint32_t X[8], Y[8], xf = 0, tprev = 0;
 #pragma unroll
   for (int i = 0; i < 8; i++) X[i] = Y[i] = 0;

@@ -85,6 +85,34 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, long long* cycles, uint3
       fb = sb200::fq_mul_inl(fb, fa);
 #pragma unroll
       for (int c = 0; c < 8; c++) { w[c] = fa.v[c]; w[8 + c] = fb.v[c]; }
+    } else if (MODE == 8 || MODE == 9) {
+      // dual-pipe probe: the carry-chain block of MODE 3 (8 wide products on the FMA-heavy pipe) interleaved with
+      // 4 independent DFMA (FP64 pipe) [and, MODE 9, 4 add.cc/addc pairs on the ALU pipe].  If the pipes are
+      // independent and power allows, the wide-product rate stays at MODE 3's.
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        uint32_t* y = w + 8 * h;
+        uint32_t mul = w[8 * (1 - h)];
+        asm volatile(
+            "mad.lo.cc.u32 %0, %8, %9, %0;\n\t"
+            "madc.hi.cc.u32 %1, %8, %9, %1;\n\t"
+            "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+            "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+            "madc.lo.cc.u32 %4, %8, %11, %4;\n\t"
+            "madc.hi.cc.u32 %5, %8, %11, %5;\n\t"
+            "madc.lo.cc.u32 %6, %8, %12, %6;\n\t"
+            "madc.hi.u32 %7, %8, %12, %7;"
+            : "+r"(y[0]), "+r"(y[1]), "+r"(y[2]), "+r"(y[3]), "+r"(y[4]), "+r"(y[5]), "+r"(y[6]), "+r"(y[7])
+            : "r"(mul), "r"(b), "r"(b1), "r"(b2), "r"(b3));
+#pragma unroll
+        for (int c = 0; c < 2; c++) asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(d[2 * h + c]) : "d"(1.0000001), "d"(1e-9));
+        if (MODE == 9) {
+#pragma unroll
+          for (int c = 0; c < 2; c++)
+            asm volatile("{\n\t.reg .u32 l,h;\n\tmov.b64 {l,h}, %0;\n\tadd.cc.u32 l, l, %1;\n\taddc.u32 h, h, %2;\n\tmov.b64 %0, {l,h};\n\t}"
+                         : "+l"(v[2 * h + c]) : "r"(a), "r"(b));
+        }
+      }
     } else if (MODE == 6) {  // DFMA
 #pragma unroll
       for (int c = 0; c < CHAINS; c++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[c]) : "d"(1.0000001), "d"(1e-9));
@@ -139,6 +167,8 @@ int main(int argc, char** argv) {
   if (run<4>("iadd64_pair", CHAINS, nsm, cps, out, cyc, false, ITERS)) return 1;  // 16 adds / iter
   if (run<5>("mix_wide4_alu8", 4, nsm, cps, out, cyc, false, ITERS)) return 1;  // counts the 4 wide products
   if (run<6>("dfma", CHAINS, nsm, cps, out, cyc, false, ITERS)) return 1;
+  if (run<8>("wide8_dfma4__wide", 8, nsm, cps, out, cyc, false, ITERS)) return 1;          // counts the 8 wide products
+  if (run<9>("wide8_dfma4_iadd4__wide", 8, nsm, cps, out, cyc, false, ITERS)) return 1;    // counts the 8 wide products
   if (run<7>("fq_mul_wide_products", 240, nsm, 4, out, cyc, true, ITERS / 16)) return 1;  // 2 muls x 120 products / iter
   printf("}\n");
   return 0;
