@@ -11,8 +11,30 @@
 #pragma once
 #include "ed.cuh"
 #include "hades.cuh"
+#include "hades_fd.cuh"
 
 namespace sb200 {
+
+// Challenge hash of the one-tuple-per-thread kernels: the IMAD.WIDE permutation of hades.cuh.  SB_HADES_FD=1 selects
+// the FP64-pipe permutation (hades_fd.cuh) instead -- same scalar; measured slower when every warp runs both halves
+// (the win comes from dedicating warps to it: k_verify_ws in schnorr_b200.cu).
+#ifndef SB_HADES_FD
+#define SB_HADES_FD 0
+#endif
+SB_HD void chal3(const fq& Ru, const fq& Rv, const fq& m, uint32_t* c) {
+#if SB_HADES_FD
+  challenge3_fd(Ru, Rv, m, c);
+#else
+  challenge3(Ru, Rv, m, c);
+#endif
+}
+SB_HD void chal5(const fq& Ru, const fq& Rv, const fq& Rpu, const fq& Rpv, const fq& m, uint32_t* c) {
+#if SB_HADES_FD
+  challenge5_fd(Ru, Rv, Rpu, Rpv, m, c);
+#else
+  challenge5(Ru, Rv, Rpu, Rpv, m, c);
+#endif
+}
 
 struct point_in {  // a point as handed over the ABI: affine (Z absent => 1) or projective (U : V : Z)
   fq U, V, Z;
@@ -47,18 +69,16 @@ SB_HD bool scalar_lt_r(const uint32_t* k) {
   return sub8(t, k, rr) != 0;  // borrow <=> k < r
 }
 
-SB_HD bool verify_core(const point_in& PK, const uint32_t* u_in, const point_in& R, const fq& m, const uint32_t* combG,
-                       uint32_t* c_out) {
-  fq ru, rv;
-  point_to_affine(R, ru, rv);
-  uint32_t c[8];
-  challenge3(ru, rv, m, c);
-#pragma unroll
-  for (int i = 0; i < 8; i++) c_out[i] = c[i];
+// the curve half of a verification: c*PK + u*G == R for a challenge computed elsewhere
+SB_HD bool verify_ec_core(const point_in& PK, const uint32_t* u_in, const point_in& R, const uint32_t* c_in,
+                          const uint32_t* combG) {
   bool ok = scalar_lt_r(u_in);
-  uint32_t u[8];
+  uint32_t u[8], c[8];
 #pragma unroll
-  for (int i = 0; i < 8; i++) u[i] = ok ? u_in[i] : 0u;
+  for (int i = 0; i < 8; i++) {
+    u[i] = ok ? u_in[i] : 0u;
+    c[i] = c_in[i];
+  }
   pniels tab[9];
   vartable_build(tab, point_to_ext(PK));
   recode_offset<4>(c);
@@ -68,12 +88,31 @@ SB_HD bool verify_core(const point_in& PK, const uint32_t* u_in, const point_in&
   return ok & p1p1_equals(cp, R);
 }
 
+// the hash half: c = H(R_affine, m)
+SB_HD void verify_hash_core(const point_in& R, const fq& m, uint32_t* c_out) {
+  fq ru, rv;
+  point_to_affine(R, ru, rv);
+  chal3(ru, rv, m, c_out);
+}
+// ... on the FP64 pipe, permutation state in caller-provided slot storage (hades_fd.cuh)
+SB_HD void verify_hash_core_fd(const point_in& R, const fq& m, uint32_t* c_out, double* slots, int ls) {
+  fq ru, rv;
+  point_to_affine(R, ru, rv);
+  challenge3_fd_p(ru, rv, m, c_out, slots, ls);
+}
+
+SB_HD bool verify_core(const point_in& PK, const uint32_t* u_in, const point_in& R, const fq& m, const uint32_t* combG,
+                       uint32_t* c_out) {
+  verify_hash_core(R, m, c_out);
+  return verify_ec_core(PK, u_in, R, c_out, combG);
+}
+
 SB_HD bool verify_vargen_core(const point_in& PK, const point_in& GEN, const uint32_t* u_in, const point_in& R,
                               const fq& m, uint32_t* c_out) {
   fq ru, rv;
   point_to_affine(R, ru, rv);
   uint32_t c[8];
-  challenge3(ru, rv, m, c);
+  chal3(ru, rv, m, c);
 #pragma unroll
   for (int i = 0; i < 8; i++) c_out[i] = c[i];
   bool ok = scalar_lt_r(u_in);
@@ -103,7 +142,7 @@ SB_HD bool verify_double_core(const point_in& PK, const point_in& PKp, const uin
     rpu = fq_mul(Rp.U, zi2); rpv = fq_mul(Rp.V, zi2);
   }
   uint32_t c[8];
-  challenge5(ru, rv, rpu, rpv, m, c);
+  chal5(ru, rv, rpu, rpv, m, c);
 #pragma unroll
   for (int i = 0; i < 8; i++) c_out[i] = c[i];
   bool ok = scalar_lt_r(u_in);
@@ -186,7 +225,7 @@ SB_HD ext var_base_mul(const point_in& P, const uint32_t* k) {
 SB_HD void sign_core(const uint32_t* sk, const uint32_t* nonce, const fq& m, const uint32_t* combG, uint32_t* u_out,
                      fq& Ru, fq& Rv, uint32_t* c_out) {
   ext_to_affine(fixed_base_mul(combG, nonce), Ru, Rv);
-  challenge3(Ru, Rv, m, c_out);
+  chal3(Ru, Rv, m, c_out);
   sign_finish(nonce, c_out, sk, u_out);
 }
 
@@ -197,14 +236,14 @@ SB_HD void sign_double_core(const uint32_t* sk, const uint32_t* nonce, const fq&
   fq zi1 = fq_mul(zi, b.Z), zi2 = fq_mul(zi, a.Z);
   Ru = fq_mul(a.X, zi1); Rv = fq_mul(a.Y, zi1);
   Rpu = fq_mul(b.X, zi2); Rpv = fq_mul(b.Y, zi2);
-  challenge5(Ru, Rv, Rpu, Rpv, m, c_out);
+  chal5(Ru, Rv, Rpu, Rpv, m, c_out);
   sign_finish(nonce, c_out, sk, u_out);
 }
 
 SB_HD void sign_vargen_core(const uint32_t* sk, const point_in& GEN, const uint32_t* nonce, const fq& m, uint32_t* u_out,
                             fq& Ru, fq& Rv, uint32_t* c_out) {
   ext_to_affine(var_base_mul(GEN, nonce), Ru, Rv);
-  challenge3(Ru, Rv, m, c_out);
+  chal3(Ru, Rv, m, c_out);
   sign_finish(nonce, c_out, sk, u_out);
 }
 

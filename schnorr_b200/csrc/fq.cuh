@@ -47,8 +47,8 @@ struct fq {
 #if !defined(__CUDA_ARCH__)
 namespace emu {
 // op counters of the host (test) build: the roofline's "work per tuple" is counted, not estimated
-struct counters { unsigned long long wide, fq_mul, fq_sqr, fq_addsub, fr_mul, fq_dot5; };
-inline counters& cnt() { static thread_local counters c = {0, 0, 0, 0, 0, 0}; return c; }
+struct counters { unsigned long long wide, fq_mul, fq_sqr, fq_addsub, fr_mul, fq_dot5, dfma, fd_mul, fd_sqr, fd_dot5; };
+inline counters& cnt() { static thread_local counters c = {}; return c; }
 #define SB_COUNT(field, k) (::sb200::emu::cnt().field += (k))
 // acc[0..n) += addend (little-endian limbs) starting at limb `at`; returns carry out of limb n-1
 static inline uint32_t add_at(uint32_t* acc, int n, int at, uint64_t val, uint32_t cin) {

@@ -48,6 +48,16 @@ struct KArgs {
   uint32_t* bitmap;
   const uint32_t* combG;
   const uint32_t* combGp;
+  struct WsState* ws;
+  int nsm;
+};
+
+// scheduling state of one warp-specialised launch (k_verify_ws): the next-tile counter, reset before every launch,
+// and one monotonic CTA-arrival counter per SM that rotates the hash-warp position among an SM's resident CTAs
+struct WsState {
+  unsigned tile;
+  unsigned pad[31];
+  unsigned sm_slot[512];
 };
 
 __device__ __forceinline__ fq ldg_fq(const uint32_t* p) {
@@ -179,7 +189,17 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
     fq s[5];
 #pragma unroll
     for (int k = 0; k < 5; k++) s[k] = ldg_fq(a.in[0] + i * 40 + k * 8);
-    if (a.aux) hades_perm_dense(s); else hades_perm(s);
+    if (a.aux == 2) {  // FP64-pipe permutation (hades_fd.cuh); same Montgomery-2^256 words in and out
+      fd t[5];
+#pragma unroll 1
+      for (int k = 0; k < 5; k++) t[k] = fd_from_fq(s[k]);
+      hades_perm_fd(t);
+#pragma unroll 1
+      for (int k = 0; k < 5; k++) {
+        fd_to_canonical(t[k], s[k].v);
+        s[k] = fq_to_mont(s[k]);
+      }
+    } else if (a.aux) hades_perm_dense(s); else hades_perm(s);
     if (active) {
 #pragma unroll
       for (int k = 0; k < 5; k++) stg8(a.out[0] + i * 40 + k * 8, s[k].v);
@@ -263,6 +283,102 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Warp-specialised single-key verification: one persistent 640-thread CTA per SM = 8 hash warps + 12 curve warps,
+// i.e. on every SM sub-partition (warp w runs on sub-partition w % 4) 2 hash warps beside 3 curve warps.
+//
+// The curve half of a verification (c*PK + u*G == R) saturates the FMA-heavy pipe with IMAD.WIDE while using ~40 %
+// of the issue slots; the Poseidon challenge on the FP64 pipe (hades_fd.cuh) needs issue slots and the FP64 / ALU
+// pipes only.  Keeping both kinds of warp on every sub-partition at all times overlaps the two: the hash warps
+// compute the challenges of the CTA's NEXT tile into shared memory while the curve warps verify the current tile.
+// A hash warp alone is latency-bound (IPC ~0.17 measured), hence two per sub-partition; the work per iteration is
+// 3 hashes per hash lane and 2 verifications per curve lane (tile = 12 x 32 x 2 = 8 x 32 x 3 = 768 tuples).
+// Tiles are handed out by a global counter; verdict words never straddle warps.
+// 96 registers per thread (20 warps per SM): the curve code measured within 2 % of its 128-register build.
+// ------------------------------------------------------------------------------------------------
+#ifndef SB_VERIFY_WS
+#define SB_VERIFY_WS 1
+#endif
+#ifndef SB_WS_SETMAXNREG
+#define SB_WS_SETMAXNREG 1
+#endif
+#ifndef SB_WS_HREGS
+#define SB_WS_HREGS 56
+#endif
+#ifndef SB_WS_EREGS
+#define SB_WS_EREGS 120
+#endif
+constexpr int WS_HW = 8, WS_EW = 12, WS_THREADS = (WS_HW + WS_EW) * 32, WS_EPER = 2;
+constexpr int WS_TILE = WS_EW * 32 * WS_EPER;       // 768 tuples per iteration
+constexpr int WS_HPER = WS_TILE / (WS_HW * 32);     // 3 hashes per hash lane
+constexpr size_t WS_SMEM = (size_t)2 * WS_TILE * 8 * sizeof(uint32_t);
+static_assert(WS_HPER * WS_HW * 32 == WS_TILE, "hash and curve warps must cover the same tile");
+__global__ void __launch_bounds__(WS_THREADS, 1) k_verify_ws(const KArgs a) {
+  extern __shared__ __align__(16) uint32_t ws_smem[];
+  uint32_t(*cbuf)[WS_TILE][8] = reinterpret_cast<uint32_t(*)[WS_TILE][8]>(ws_smem);
+  __shared__ unsigned tiles[2];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool aff = (a.flags & SB200_POINTS_AFFINE) != 0;
+  const unsigned ntiles = (unsigned)((a.n + WS_TILE - 1) / WS_TILE);
+  if (tid == 0) tiles[0] = atomicAdd(&a.ws->tile, 1u);
+  __syncthreads();
+  const bool is_hash = warp < WS_HW;
+#if SB_WS_SETMAXNREG
+  // register re-partitioning between warpgroups: the hash warps give up what the curve warps need
+  if (is_hash) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SB_WS_HREGS));
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SB_WS_EREGS));
+#endif
+
+  auto hash_tile = [&](unsigned t, uint32_t (*buf)[8]) {
+#pragma unroll 1
+    for (int s = 0; s < WS_HPER; s++) {
+      const int local = (s * WS_HW + warp) * 32 + lane;
+      int64_t i = (int64_t)t * WS_TILE + local;
+      const bool act = i < a.n;
+      if (!act) i = a.n - 1;
+      uint32_t c[8];
+      fq ru, rv;
+      point_to_affine(ldg_point(a.in[2], i, aff), ru, rv);
+      challenge3_fd(ru, rv, ldg_fq(a.in[3] + i * 8), c);
+      stg8(buf[local], c);
+      if (a.out[0] && act) stg8(a.out[0] + i * 8, c);
+    }
+  };
+
+  int cur = 0;
+  if (is_hash && tiles[0] < ntiles) hash_tile(tiles[0], cbuf[0]);
+  if (tid == 0) tiles[1] = atomicAdd(&a.ws->tile, 1u);
+  __syncthreads();
+  while (tiles[cur] < ntiles) {
+    const unsigned t = tiles[cur], tn = tiles[cur ^ 1];
+    if (is_hash) {
+      if (tn < ntiles) hash_tile(tn, cbuf[cur ^ 1]);
+    } else {
+#pragma unroll 1
+      for (int s = 0; s < WS_EPER; s++) {
+        const int local0 = (s * WS_EW + (warp - WS_HW)) * 32;
+        const int64_t i0 = (int64_t)t * WS_TILE + local0;
+        if (i0 >= a.n) break;  // warp-uniform
+        int64_t i = i0 + lane;
+        const bool act = i < a.n;
+        if (!act) i = a.n - 1;
+        uint32_t u[8], c[8];
+        ldg_scalar(a.in[1] + i * 8, u);
+        const uint4* cp = reinterpret_cast<const uint4*>(cbuf[cur][act ? local0 + lane : local0]);
+        uint4 c0 = cp[0], c1 = cp[1];
+        c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+        bool ok = verify_ec_core(ldg_point(a.in[0], i, aff), u, ldg_point(a.in[2], i, aff), c, a.combG);
+        unsigned word = __ballot_sync(0xffffffffu, ok && act);
+        if (lane == 0) a.bitmap[i0 >> 5] = word;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) tiles[cur] = atomicAdd(&a.ws->tile, 1u);
+    cur ^= 1;
+    __syncthreads();
+  }
+}
+
 // Fixed-base signing / key generation with several tuples per thread: the scalar multiples of G (and G') are
 // computed first, all their Z coordinates are inverted together (one field inversion per thread instead of one
 // per point: the inversion is a third of a single signature's work), then each tuple is finished.
@@ -313,7 +429,7 @@ __global__ void __launch_bounds__(TPB, 4) k_fixed_batch(const KArgs a) {
     ldg_scalar(a.in[2] + i * 8, nonce);
     fq m = ldg_fq(a.in[1] + i * 8);
     if (OP == OP_SIGN_BYTES) m = fq_to_mont(m);
-    if (DOUBLE) challenge5(Ru, Rv, Rpu, Rpv, m, c); else challenge3(Ru, Rv, m, c);
+    if (DOUBLE) chal5(Ru, Rv, Rpu, Rpv, m, c); else chal3(Ru, Rv, m, c);
     sign_finish(nonce, c, sk, u);
     if (!active) continue;
     if (OP == OP_SIGN_BYTES) {
@@ -347,6 +463,8 @@ struct DevCtx {
   uint32_t* combGp = nullptr;
   uint8_t* arena[2] = {nullptr, nullptr};
   size_t arena_cap[2] = {0, 0};
+  WsState* ws[3] = {nullptr, nullptr, nullptr};  // per pipeline stream, [2] = caller's stream (SB200_DEVICE_PTRS)
+  int nsm = 0;
 };
 
 struct Desc {
@@ -386,6 +504,17 @@ int launch(sb200_ctx* ctx, Op op, const KArgs& a, cudaStream_t st) {
   if (a.n <= 0) return SB200_OK;
   unsigned grid = (unsigned)((a.n + TPB - 1) / TPB);
   unsigned gridk = (unsigned)((a.n + TPB * SIGN_K - 1) / (TPB * SIGN_K));
+#if SB_VERIFY_WS
+  if (op == OP_VERIFY && a.n >= 2 * (int64_t)WS_TILE * a.nsm) {  // persistent warp-specialised kernel, one CTA per SM (small batches: k_run)
+    CU(cudaMemsetAsync(&a.ws->tile, 0, sizeof(unsigned), st));
+    unsigned ntiles = (unsigned)((a.n + WS_TILE - 1) / WS_TILE);
+    unsigned g = std::min<unsigned>(ntiles, (unsigned)a.nsm);
+    k_verify_ws<<<g, WS_THREADS, WS_SMEM, st>>>(a);
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    CU(cudaGetLastError());
+    return SB200_OK;
+  }
+#endif
   switch (op) {
 #define CASEK(O) case O: k_fixed_batch<O><<<gridk, TPB, 0, st>>>(a); break;
     CASEK(OP_SIGN) CASEK(OP_SIGN_DOUBLE) CASEK(OP_KEYGEN) CASEK(OP_KEYGEN_DOUBLE) CASEK(OP_SIGN_BYTES)
@@ -417,6 +546,7 @@ int run(sb200_ctx* ctx, int64_t n, const Desc& d) {
     CU(cudaSetDevice(dc.dev));
     KArgs a{};
     a.n = n; a.flags = d.flags; a.aux = d.aux; a.combG = dc.combG; a.combGp = dc.combGp; a.bitmap = d.bitmap;
+    a.ws = dc.ws[2]; a.nsm = dc.nsm;
     for (int k = 0; k < d.nin; k++) a.in[k] = d.in[k];
     for (int k = 0; k < d.nout; k++) a.out[k] = d.out[k];
     return launch(ctx, d.op, a, ctx->user_stream);
@@ -451,6 +581,7 @@ int run(sb200_ctx* ctx, int64_t n, const Desc& d) {
       auto carve = [&](size_t bytes) { uint8_t* r = p; p += (bytes + 63) & ~(size_t)63; return r; };
       KArgs a{};
       a.n = cn; a.flags = d.flags; a.aux = d.aux; a.combG = dc.combG; a.combGp = dc.combGp;
+      a.ws = dc.ws[slot]; a.nsm = dc.nsm;
       for (int k = 0; k < d.nin; k++) {
         if (!d.in_words[k]) continue;
         size_t bytes = (size_t)cn * d.in_words[k] * 4;
@@ -510,6 +641,11 @@ int sb200_init(const int* devices, int n_devices, sb200_ctx** out) {
       if (cudaStreamCreateWithFlags(&dc.stream[s], cudaStreamNonBlocking) != cudaSuccess) return fail(SB200_ERR_CUDA);
     size_t tb = (size_t)COMB_WINDOWS * COMB_ENTRIES * 24 * 4;
     if (cudaMalloc(&dc.combG, tb) != cudaSuccess || cudaMalloc(&dc.combGp, tb) != cudaSuccess) return fail(SB200_ERR_NOMEM);
+    dc.nsm = prop.multiProcessorCount;
+    if (cudaFuncSetAttribute(k_verify_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM) != cudaSuccess) return fail(SB200_ERR_CUDA);
+    for (int s = 0; s < 3; s++)
+      if (cudaMalloc(&dc.ws[s], sizeof(WsState)) != cudaSuccess || cudaMemset(dc.ws[s], 0, sizeof(WsState)) != cudaSuccess)
+        return fail(SB200_ERR_NOMEM);
     ctx->devs.push_back(dc);
     int grid = (COMB_WINDOWS * COMB_ENTRIES + TPB - 1) / TPB;
     k_comb_build<<<grid, TPB, 0, dc.stream[0]>>>(dc.combG, 0);
@@ -531,6 +667,8 @@ void sb200_destroy(sb200_ctx* ctx) {
     }
     if (dc.combG) cudaFree(dc.combG);
     if (dc.combGp) cudaFree(dc.combGp);
+    for (int s = 0; s < 3; s++)
+      if (dc.ws[s]) cudaFree(dc.ws[s]);
   }
   delete ctx;
 }

@@ -10,8 +10,8 @@ static fq L(const uint32_t* p) { fq r; memcpy(r.v, p, 32); return r; }
 static void S(uint32_t* p, const fq& a) { memcpy(p, a.v, 32); }
 
 extern "C" {
-void h_counts_reset() { emu::cnt() = {0, 0, 0, 0, 0, 0}; }
-void h_counts_get(unsigned long long* o) { auto& c = emu::cnt(); o[0] = c.wide; o[1] = c.fq_mul; o[2] = c.fq_sqr; o[3] = c.fq_addsub; o[4] = c.fr_mul; o[5] = c.fq_dot5; }
+void h_counts_reset() { emu::cnt() = {}; }
+void h_counts_get(unsigned long long* o) { auto& c = emu::cnt(); o[0] = c.wide; o[1] = c.fq_mul; o[2] = c.fq_sqr; o[3] = c.fq_addsub; o[4] = c.fr_mul; o[5] = c.fq_dot5; o[6] = c.dfma; o[7] = c.fd_mul; o[8] = c.fd_sqr; o[9] = c.fd_dot5; }
 void h_fq_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { S(r, fq_mul(L(a), L(b))); }
 void h_fq_sqr(const uint32_t* a, uint32_t* r) { S(r, fq_sqr(L(a))); }
 void h_fq_dot5(const uint32_t* c40, const uint32_t* s40, uint32_t* r) {
@@ -22,6 +22,36 @@ void h_fq_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { S(r, fq_sub(L
 void h_fq_inv(const uint32_t* a, uint32_t* r) { S(r, fq_inv(L(a))); }
 void h_fr_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) {
   fr x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); fr z = fr_mul(x, y); memcpy(r, z.v, 32);
+}
+// ---- FP64-pipe arithmetic (fd.cuh / hades_fd.cuh), DFMA pair emulated by a 128-bit product --------------------
+static fdd FD(const uint32_t* p) { return fd_todbl(fd_split(p)); }   // plain 256-bit integer, limbs re-sliced
+static void FS(uint32_t* p, const fd& a) { fd_join(a, p); }           // lazily reduced result (< 2^256)
+void h_fd_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { FS(r, fd_mul(FD(a), FD(b))); }
+void h_fd_sqr(const uint32_t* a, uint32_t* r) { FS(r, fd_sqr(FD(a))); }
+void h_fd_mulc_add(const uint32_t* cst, const uint32_t* x, const uint32_t* c, uint32_t* r) {
+  fdd cd = FD(cst);
+  FS(r, fd_mulc_add(cd.d, FD(x), fd_split(c)));
+}
+void h_fd_dot5(const uint32_t* c40, const uint32_t* s40, const uint32_t* add, uint32_t* r) {
+  double cst[25];
+  for (int j = 0; j < 5; j++) { fdd t = FD(c40 + 8 * j); for (int k = 0; k < 5; k++) cst[5 * j + k] = t.d[k]; }
+  fd ad; if (add) ad = fd_split(add);
+  FS(r, fd_dot5(cst, add ? ad.l : nullptr, FD(s40), FD(s40 + 8), FD(s40 + 16), FD(s40 + 24), FD(s40 + 32)));
+}
+void h_fd_roundtrip(const uint32_t* a, uint32_t* r) { fd_to_canonical(fd_from_fq(L(a)), r); }  // Montgomery-256 in, canonical out
+void h_hades_fd(uint32_t* st) {  // Montgomery-256 words in, canonical integers out
+  fd s[5]; for (int i = 0; i < 5; i++) s[i] = fd_from_fq(L(st + 8 * i));
+  hades_perm_fd(s);
+  for (int i = 0; i < 5; i++) fd_to_canonical(s[i], st + 8 * i);
+}
+void h_challenge3(const uint32_t* ru, const uint32_t* rv, const uint32_t* m, int fdpath, uint32_t* c) {
+  double slots[FDH_SLOTS * 10 * 3];
+  if (fdpath == 2) challenge3_fd_p(L(ru), L(rv), L(m), c, slots, 1);
+  else if (fdpath == 3) challenge3_fd_p(L(ru), L(rv), L(m), c, slots + 1, 3);  // strided layout
+  else if (fdpath) challenge3_fd(L(ru), L(rv), L(m), c); else challenge3(L(ru), L(rv), L(m), c);
+}
+void h_challenge5(const uint32_t* ru, const uint32_t* rv, const uint32_t* rpu, const uint32_t* rpv, const uint32_t* m, int fdpath, uint32_t* c) {
+  if (fdpath) challenge5_fd(L(ru), L(rv), L(rpu), L(rpv), L(m), c); else challenge5(L(ru), L(rv), L(rpu), L(rpv), L(m), c);
 }
 void h_hades(uint32_t* st, int dense) {
   fq s[5]; for (int i = 0; i < 5; i++) s[i] = L(st + 8 * i);

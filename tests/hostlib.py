@@ -13,7 +13,7 @@ RADIX = 1 << 256
 def build():
     so = os.path.join(ROOT, "build", "host_arith.so")
     src = os.path.join(ROOT, "tests", "host_arith.cpp")
-    hdrs = [os.path.join(ROOT, "schnorr_b200", "csrc", f) for f in ("fq.cuh", "ed.cuh", "hades.cuh", "core.cuh", "wire.cuh", "constants_gen.cuh")]
+    hdrs = [os.path.join(ROOT, "schnorr_b200", "csrc", f) for f in ("fq.cuh", "fd.cuh", "ed.cuh", "hades.cuh", "hades_fd.cuh", "core.cuh", "wire.cuh", "constants_gen.cuh")]
     newest = max(os.path.getmtime(p) for p in [src] + hdrs)
     if not os.path.exists(so) or os.path.getmtime(so) < newest:
         os.makedirs(os.path.dirname(so), exist_ok=True)

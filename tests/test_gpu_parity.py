@@ -47,7 +47,7 @@ def test_fr_mul(engine):
     assert V.ints_out(engine.dbg_fr_mul(V.scalars(xs), V.scalars(ys))) == [x * y % R for x, y in zip(xs, ys)]
 
 
-@pytest.mark.parametrize("dense", [True, False])
+@pytest.mark.parametrize("dense", [True, False, 2], ids=["dense", "sparse", "fd"])
 def test_hades(engine, dense):
     rnd = random.Random(14)
     states = [[0] * 5, [1] * 5, [Q - 1] * 5, [0, 1, 2, 3, 4]] + [[rnd.randrange(Q) for _ in range(5)] for _ in range(60)]

@@ -159,3 +159,74 @@ def test_wire_formats(lib, tabs):
     assert lib.h_verify_bytes(B(pkb), B(sig), B(Q.to_bytes(32, "little")), H.ptr(tabs[0]), ctypes.byref(inv)) == 0 and inv.value == 1
     bad_sig = (u + R).to_bytes(32, "little") + o.affine_to_bytes(Rp)
     assert lib.h_verify_bytes(B(pkb), B(bad_sig), B(m.to_bytes(32, "little")), H.ptr(tabs[0]), ctypes.byref(inv)) == 0 and inv.value == 1
+
+
+# ---- FP64-pipe arithmetic (csrc/fd.cuh, hades_fd.cuh): 5 x 52-bit limbs, Montgomery radix 2^260 ----------------
+R260INV = pow(1 << 260, -1, Q)
+
+
+def test_fd_mul_sqr_mulc_add(lib):
+    rnd = random.Random(11)
+    out = np.zeros(8, np.uint32)
+    top = (1 << 256) - 1  # lazily reduced operands (the test hooks carry 256-bit integers)
+    vals = [0, 1, 2, Q - 1, Q, Q + 1, 2 * Q - 1, top, (1 << 255), (1 << 52) - 1, 1 << 52, ((1 << 52) - 1) << 52,
+            sum(((1 << 52) - 1) << (52 * i) for i in range(4)) | (((1 << 48) - 1) << 208)] + [rnd.randrange(top) for _ in range(50)]
+    for a in vals:
+        lib.h_fd_sqr(H.ptr(H.limbs(a)), H.ptr(out))
+        r = H.to_int(out)
+        assert r % Q == a * a * R260INV % Q and r < a * a // (1 << 260) + Q + 1
+        for b in vals[:20]:
+            lib.h_fd_mul(H.ptr(H.limbs(a)), H.ptr(H.limbs(b)), H.ptr(out))
+            r = H.to_int(out)
+            assert r % Q == a * b * R260INV % Q and r < a * b // (1 << 260) + Q + 1
+    # constant * x + running word, with the one conditional subtraction of q (word >= 2^255)
+    topc = (1 << 256) - (1 << 251)
+    for _ in range(300):
+        cst, x = rnd.randrange(Q), rnd.randrange(2 * Q)
+        c = rnd.choice([0, (1 << 255) - 1, 1 << 255, Q, topc, rnd.randrange(topc), rnd.randrange(Q)])  # result must fit the 256-bit hook
+        lib.h_fd_mulc_add(H.ptr(H.limbs(cst)), H.ptr(H.limbs(x)), H.ptr(H.limbs(c)), H.ptr(out))
+        r = H.to_int(out)
+        cp = c - Q if c >= (1 << 255) else c
+        assert r % Q == (cst * x * R260INV + c) % Q and cp <= r < cst * x // (1 << 260) + Q + 1 + cp
+
+
+def test_fd_dot5_and_roundtrip(lib):
+    rnd = random.Random(12)
+    out = np.zeros(8, np.uint32)
+    top = (1 << 256) - 1
+    cases = [([Q - 1] * 5, [top] * 5, Q - 1), ([0] * 5, [top] * 5, 0), ([1, 0, 0, 0, 0], [5, 0, 0, 0, 0], None)]
+    cases += [([rnd.randrange(Q) for _ in range(5)], [rnd.randrange(top) for _ in range(5)], rnd.choice([None, rnd.randrange(Q)])) for _ in range(200)]
+    for c, s, add in cases:
+        cb = np.concatenate([H.limbs(x) for x in c]); sb = np.concatenate([H.limbs(x) for x in s])
+        lib.h_fd_dot5(H.ptr(cb), H.ptr(sb), H.ptr(H.limbs(add)) if add is not None else None, H.ptr(out))
+        r = H.to_int(out)
+        assert r % Q == (sum(a * b for a, b in zip(c, s)) * R260INV + (add or 0)) % Q
+        assert r < sum(a * b for a, b in zip(c, s)) // (1 << 260) + Q + 1 + (add or 0)
+    for a in [0, 1, Q - 1, Q - 2, 1 << 254] + [rnd.randrange(Q) for _ in range(100)]:
+        lib.h_fd_roundtrip(H.ptr(H.mont(a)), H.ptr(out))
+        assert H.to_int(out) == a
+
+
+def test_hades_fd_matches_oracle(lib):
+    rnd = random.Random(13)
+    for st in [[0] * 5, [Q - 1] * 5, [1, 2, 3, 4, 5]] + [[rnd.randrange(Q) for _ in range(5)] for _ in range(6)]:
+        buf = np.concatenate([H.mont(x) for x in st])
+        lib.h_hades_fd(H.ptr(buf))
+        assert [H.to_int(buf[8 * i:8 * i + 8]) for i in range(5)] == o.hades_perm(st)
+
+
+def test_challenge_fd_matches_imad_path_and_oracle(lib):
+    rnd = random.Random(14)
+    c0, c1 = np.zeros(8, np.uint32), np.zeros(8, np.uint32)
+    for _ in range(6):
+        P1, P2 = V.mul(o.G, rnd.randrange(R)), V.mul(o.G_NUMS, rnd.randrange(R))
+        m = rnd.choice([0, Q - 1, rnd.randrange(Q)])
+        args = [H.ptr(H.mont(P1[0])), H.ptr(H.mont(P1[1])), H.ptr(H.mont(m))]
+        lib.h_challenge3(*args, 0, H.ptr(c0)); lib.h_challenge3(*args, 1, H.ptr(c1))
+        assert H.to_int(c0) == H.to_int(c1) == o.challenge_hash(P1, m)
+        for mode in (2, 3):  # memory-operand permutation, dense and strided slot layouts
+            lib.h_challenge3(*args, mode, H.ptr(c1))
+            assert H.to_int(c1) == H.to_int(c0)
+        args = [H.ptr(H.mont(P1[0])), H.ptr(H.mont(P1[1])), H.ptr(H.mont(P2[0])), H.ptr(H.mont(P2[1])), H.ptr(H.mont(m))]
+        lib.h_challenge5(*args, 0, H.ptr(c0)); lib.h_challenge5(*args, 1, H.ptr(c1))
+        assert H.to_int(c0) == H.to_int(c1) == o.challenge_hash_double(P1, P2, m)

@@ -36,6 +36,26 @@ def inv(x):
     return pow(x, -1, Q)
 
 
+# ---- FP64-pipe representation (csrc/fd.cuh): 5 x 52-bit limbs, Montgomery radix 2^260 ------------
+RADIX260 = 1 << 260
+
+
+def limbs52(x):
+    return [(x >> (52 * i)) & ((1 << 52) - 1) for i in range(5)]
+
+
+def m260(x):
+    return x * RADIX260 % Q
+
+
+def fmt_d(x):  # operand form: limbs as exactly representable doubles
+    return "{" + ", ".join("%d.0" % w for w in limbs52(x)) + "}"
+
+
+def fmt_u(x):  # integer form
+    return "{" + ", ".join("0x%013xull" % w for w in limbs52(x)) + "}"
+
+
 # ---- Hades252 (dusk-hades): round constants and MDS --------------------------------------
 def round_constants():
     out, b = [], b"poseidon-for-plonk"
@@ -274,6 +294,42 @@ def main():
     for i in range(WIDTH):
         for j in range(WIDTH):
             w("  %s, \\" % fmt(mont(post[i][j])))
+    w("}")
+    w("// FP64-pipe field arithmetic (csrc/fd.cuh): 5 x 52-bit limbs, Montgomery radix 2^260")
+    w("#define SB200_FD_Q_D_INIT %s" % fmt_d(Q))
+    w("#define SB200_FD_Q_U_INIT %s" % fmt_u(Q))
+    w("#define SB200_FD_KIN_D_INIT %s   // 2^264 mod q: mont260(x * 2^256, .) = x * 2^260" % fmt_d((1 << 264) % Q))
+    w("#define SB200_FD_ONE_U_INIT %s   // 2^260 mod q" % fmt_u(RADIX260 % Q))
+    assert Q % (1 << 52) == (1 << 52) - (1 << 32) + 1 and (Q * (1 + (1 << 32))) % (1 << 52) == 1
+    w("// Hades252 tables for hades_fd.cuh, Montgomery-2^260: 9 groups of 5 additive words")
+    groups = [RC[0:5], RC[5:10], RC[10:15], RC[15:20], list(pre_add[:4]) + [ks[0]],
+              RC[63 * 5:64 * 5], RC[64 * 5:65 * 5], RC[65 * 5:66 * 5], RC[66 * 5:67 * 5]]
+    w("#define SB200_FDH_ADD_INIT { \\")
+    for g in groups:
+        for x in g:
+            w("  %s, \\" % fmt_u(m260(x)))
+    w("}")
+    w("#define SB200_FDH_MDS_INIT { \\")
+    for i in range(WIDTH):
+        for j in range(WIDTH):
+            w("  %s, \\" % fmt_d(m260(MDS[i][j])))
+    w("}")
+    w("#define SB200_FDH_POST_INIT { \\")
+    for i in range(WIDTH):
+        for j in range(WIDTH):
+            w("  %s, \\" % fmt_d(m260(post[i][j])))
+    w("}")
+    w("// per sparse round t: the key of round t + 1 (carried by the row product), then row[0..4], col[0..3]")
+    w("#define SB200_FDH_SP_ADD_INIT { \\")
+    for t in range(PARTIAL):
+        w("  %s, \\" % fmt_u(m260(ks[t + 1]) if t + 1 < PARTIAL else 0))
+    w("}")
+    w("#define SB200_FDH_SP_MAT_INIT { \\")
+    for t in range(PARTIAL):
+        for j in range(WIDTH):
+            w("  %s, \\" % fmt_d(m260(rows[t][j])))
+        for j in range(WIDTH - 1):
+            w("  %s, \\" % fmt_d(m260(cols[t][j])))
     w("}")
     w("}  // namespace sb200")
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "schnorr_b200", "csrc", "constants_gen.cuh")

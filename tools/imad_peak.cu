@@ -113,6 +113,12 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, long long* cycles, uint3
                          : "+l"(v[2 * h + c]) : "r"(a), "r"(b));
         }
       }
+    } else if (MODE == 10) {  // DFMA.RZ (the rounding mode the 52-bit-limb product trick needs)
+#pragma unroll
+      for (int c = 0; c < CHAINS; c++) asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(d[c]) : "d"(1.0000001), "d"(1e-9));
+    } else if (MODE == 11) {  // DADD
+#pragma unroll
+      for (int c = 0; c < CHAINS; c++) asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(d[c]) : "d"(1e-9));
     } else if (MODE == 6) {  // DFMA
 #pragma unroll
       for (int c = 0; c < CHAINS; c++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[c]) : "d"(1.0000001), "d"(1e-9));
@@ -167,6 +173,8 @@ int main(int argc, char** argv) {
   if (run<4>("iadd64_pair", CHAINS, nsm, cps, out, cyc, false, ITERS)) return 1;  // 16 adds / iter
   if (run<5>("mix_wide4_alu8", 4, nsm, cps, out, cyc, false, ITERS)) return 1;  // counts the 4 wide products
   if (run<6>("dfma", CHAINS, nsm, cps, out, cyc, false, ITERS)) return 1;
+  if (run<10>("dfma_rz", CHAINS, nsm, cps, out, cyc, false, ITERS)) return 1;
+  if (run<11>("dadd", CHAINS, nsm, cps, out, cyc, false, ITERS)) return 1;
   if (run<8>("wide8_dfma4__wide", 8, nsm, cps, out, cyc, false, ITERS)) return 1;          // counts the 8 wide products
   if (run<9>("wide8_dfma4_iadd4__wide", 8, nsm, cps, out, cyc, false, ITERS)) return 1;    // counts the 8 wide products
   if (run<7>("fq_mul_wide_products", 240, nsm, 4, out, cyc, true, ITERS / 16)) return 1;  // 2 muls x 120 products / iter

@@ -15,7 +15,7 @@ want = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread",
         "l1tex__t_sector_pipe_lsu_mem_local_op_ld_hit_rate.pct"]
 for r in rows[2:]:
     d = dict(zip(hdr, r))
-    for k in want:
+    for k in want + [h for h in hdr if "fp64" in h and ("pct" in h or h.endswith(".sum"))]:
         if k in d:
             print(f"{k:75s} {d[k]:>22s} {units[hdr.index(k)]}")
     print("-- stall reasons (warps stalled per issue-active cycle) --")

@@ -38,7 +38,7 @@ u, Rp, c = o.sign(sk, nonce, m, mul=V.mul)
 pk = V.mul(o.G, sk)
 fill(u)
 fill(o.sign_double(sk, nonce, m, mul=V.mul)[0])
-cnt = np.zeros(6, np.uint64)
+cnt = np.zeros(10, np.uint64)
 buf = np.zeros(8, np.uint32)
 
 def measure(fn):
