@@ -5,4 +5,4 @@ Layout: `csrc/` holds the CUDA kernels and the C ABI (`include/schnorr_b200.h`);
 (SecretKey, PublicKey, Signature, the Double and VarGen variants) on top of it.
 There is no CPU fallback anywhere in this package.
 """
-from ._lib import DEVICE_PTRS, POINTS_AFFINE, POINTS_PROJECTIVE, Engine, SchnorrB200Error, load_library  # noqa: F401
+from ._lib import DEVICE_PTRS, POINTS_AFFINE, POINTS_PROJECTIVE, VERIFY_DUAL_PIPE, Engine, SchnorrB200Error, load_library  # noqa: F401

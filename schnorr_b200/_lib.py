@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("SB200_LIB", os.path.join(_HERE, "libschnorr_b200.so")
 POINTS_PROJECTIVE = 0
 POINTS_AFFINE = 1
 DEVICE_PTRS = 2
+VERIFY_DUAL_PIPE = 4  # sb200_verify: warp-specialised kernel (hash warps on the FP64 pipe beside curve warps)
 
 _lib = None
 
@@ -155,9 +156,9 @@ class Engine:
     def _unpack_bits(bitmap: np.ndarray, n: int) -> np.ndarray:
         return np.unpackbits(bitmap.view(np.uint8), bitorder="little")[:n].astype(bool)
 
-    def verify(self, pk, u, R, msg, affine=True, want_c=True):
+    def verify(self, pk, u, R, msg, affine=True, want_c=True, dual_pipe=False):
         n = np.asarray(u).size // 8
-        pw, fl = self._pw(affine), POINTS_AFFINE if affine else POINTS_PROJECTIVE
+        pw, fl = self._pw(affine), (POINTS_AFFINE if affine else POINTS_PROJECTIVE) | (VERIFY_DUAL_PIPE if dual_pipe else 0)
         pk, u, R, msg = _arr(pk, pw, n, "pk"), _arr(u, 8, n, "u"), _arr(R, pw, n, "R"), _arr(msg, 8, n, "msg")
         bm = aligned_empty(((n + 31) // 32,)); bm[...] = 0
         c = aligned_empty((n, 8)) if want_c else None

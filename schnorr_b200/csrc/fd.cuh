@@ -295,6 +295,115 @@ SB_HD fd fd_add(const fd& a, const uint64_t* b) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Two-lane ("paired") primitives: the same operations on two independent elements in one call.  A hash warp runs
+// alone on its pipes (the other warps of its sub-partition are curve warps), so nothing hides the latency of the
+// DFMA -> DADD -> DFMA -> IADD3 chains and of the five serial rows of a reduction: a single stream measured
+// IPC 0.17 with 35-50 % `wait` stalls.  Two independent streams in the same basic block let ptxas interleave them.
+// ------------------------------------------------------------------------------------------------
+struct fd2 { fd a, b; };
+struct fdd2 { fdd a, b; };
+struct fdc2 { fdc a, b; };
+
+SB_HD fdd2 fd_todbl2(const fd2& x) { return {fd_todbl(x.a), fd_todbl(x.b)}; }
+SB_HD fdc2 fd_cols_init2(int nprod) { return {fd_cols_init(nprod), fd_cols_init(nprod)}; }
+
+SB_HD fdc2 fd_macc2_inl(fdc2 c, const fdd2& x, const double* cst) {  // c += x * constant (same constant for both)
+  fdd y = fd_ld(cst);
+  fd_mac(c.a.c, x.a.d, y.d);
+  fd_mac(c.b.c, x.b.d, y.d);
+  return c;
+}
+SB_HD fdc2 fd_macv2_inl(fdc2 c, const fdd2& x, const fdd2& y) {  // c += x * y
+  fd_mac(c.a.c, x.a.d, y.a.d);
+  fd_mac(c.b.c, x.b.d, y.b.d);
+  return c;
+}
+SB_HD fdc2 fd_sqr_cols2_inl(const fdd2& x) { return {fd_sqr_cols_inl(x.a), fd_sqr_cols_inl(x.b)}; }
+SB_HD fd2 fd_reduce2_inl(fdc2 c) {
+  // the two reductions interleaved row by row (each row's Montgomery factor depends on the previous row)
+  double q[5];
+  fd_q_dbl(q);
+  uint64_t* col[2] = {c.a.c, c.b.c};
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+      uint64_t t = col[w][i];
+      uint64_t m = (0ull - (t + (t << 32))) & FD_M52;
+      double md = fd_todbl(m);
+      uint64_t h, l, ph;
+      fd_prod(md, q[0], ph, l);
+      col[w][i] += l;
+#pragma unroll
+      for (int j = 1; j < 5; j++) {
+        fd_prod(md, q[j], h, l);
+        col[w][i + j] += ph + l;
+        ph = h;
+      }
+      col[w][i + 5] += ph;
+      col[w][i + 1] += col[w][i] >> 52;
+    }
+  }
+  fd2 r;
+  fd* rr[2] = {&r.a, &r.b};
+#pragma unroll
+  for (int w = 0; w < 2; w++) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      rr[w]->l[k] = col[w][5 + k] & FD_M52;
+      col[w][6 + k] += (uint64_t)((int64_t)col[w][5 + k] >> 52);
+    }
+    rr[w]->l[4] = col[w][9];
+  }
+  return r;
+}
+#if defined(__CUDACC__)
+static __device__ __noinline__ fdc2 fd_macc2_ool(fdc2 c, fdd2 x, const double* cst) { return fd_macc2_inl(c, x, cst); }
+static __device__ __noinline__ fdc2 fd_macv2_ool(fdc2 c, fdd2 x, fdd2 y) { return fd_macv2_inl(c, x, y); }
+static __device__ __noinline__ fdc2 fd_sqr_cols2_ool(fdd2 x) { return fd_sqr_cols2_inl(x); }
+static __device__ __noinline__ fd2 fd_reduce2_ool(fdc2 c) { return fd_reduce2_inl(c); }
+#endif
+SB_HD fdc2 fd_macc2(const fdc2& c, const fdd2& x, const double* cst) {
+#if defined(__CUDA_ARCH__)
+  return fd_macc2_ool(c, x, cst);
+#else
+  return fd_macc2_inl(c, x, cst);
+#endif
+}
+SB_HD fdc2 fd_macv2(const fdc2& c, const fdd2& x, const fdd2& y) {
+#if defined(__CUDA_ARCH__)
+  return fd_macv2_ool(c, x, y);
+#else
+  return fd_macv2_inl(c, x, y);
+#endif
+}
+SB_HD fdc2 fd_sqr_cols2(const fdd2& x) {
+#if defined(__CUDA_ARCH__)
+  return fd_sqr_cols2_ool(x);
+#else
+  return fd_sqr_cols2_inl(x);
+#endif
+}
+SB_HD fd2 fd_reduce2(const fdc2& c) {
+#if defined(__CUDA_ARCH__)
+  return fd_reduce2_ool(c);
+#else
+  return fd_reduce2_inl(c);
+#endif
+}
+// addend (+ the conditional subtraction of q, see fd_mulc_add) into the upper columns
+SB_HD void fd_cols_add(fdc& col, const uint64_t* add) {
+#pragma unroll
+  for (int k = 0; k < 5; k++) col.c[5 + k] += add[k];
+}
+SB_HD void fd_cols_add_csub(fdc& col, const fd& c) {
+  const uint64_t qu[5] = SB200_FD_Q_U_INIT;
+  const uint64_t mask = (c.l[4] >> 47) ? ~0ull : 0ull;
+#pragma unroll
+  for (int k = 0; k < 5; k++) col.c[5 + k] += c.l[k] - (qu[k] & mask);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Memory-operand form of the same primitives.  A "slot" holds one field element in both forms: doubles at
 // p[k * ls] (k < 5) and integer limbs at ((uint64_t*)p)[(5 + k) * ls]; ls = 32 for lane-strided shared memory
 // (conflict-free: consecutive lanes, consecutive 8-byte words), 1 for a thread-private array.  Operands and

@@ -81,6 +81,71 @@ SB_HD void hades_perm_fd(fd* s) {
   }
 }
 
+// ---- two permutations per thread, interleaved (fd.cuh "paired" primitives) -------------------------------------
+SB_HD fd2 fd_pow5_2(const fd2& x) {
+  fdd2 xd = fd_todbl2(x);
+  fd2 x2 = fd_reduce2(fd_sqr_cols2(xd));
+  fd2 x4 = fd_reduce2(fd_sqr_cols2(fd_todbl2(x2)));
+  return fd_reduce2(fd_macv2(fd_cols_init2(1), fd_todbl2(x4), xd));
+}
+SB_HD void fdh_matmul2(fd2* s, const double (*mat)[5], const uint64_t (*add)[5]) {
+  fdd2 d[5];
+#pragma unroll
+  for (int k = 0; k < 5; k++) d[k] = fd_todbl2(s[k]);
+#pragma unroll 1
+  for (int r = 0; r < 5; r++) {
+    fdc2 c = fd_cols_init2(5);
+    if (add) {
+      fd_cols_add(c.a, add[r]);
+      fd_cols_add(c.b, add[r]);
+    }
+#pragma unroll
+    for (int j = 0; j < 5; j++) c = fd_macc2(c, d[j], &mat[5 * r + j][0]);
+    s[r] = fd_reduce2(c);
+  }
+}
+SB_HD void hades_perm_fd2(fd2* s) {
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    s[k].a = fd_add(s[k].a, SB_CONST(fdh_add)[k]);
+    s[k].b = fd_add(s[k].b, SB_CONST(fdh_add)[k]);
+  }
+#pragma unroll 1
+  for (int r = 0; r < 4; r++) {
+#pragma unroll 1
+    for (int k = 0; k < 5; k++) s[k] = fd_pow5_2(s[k]);
+    fdh_matmul2(s, SB_CONST(fdh_mds), &SB_CONST(fdh_add)[5 * (r + 1)]);
+  }
+#pragma unroll 1
+  for (int t = 0; t < 59; t++) {
+    const double(*m)[5] = &SB_CONST(fdh_sp_mat)[9 * t];
+    fdd2 x = fd_todbl2(fd_pow5_2(s[4]));
+    {
+      fdc2 c = fd_cols_init2(5);
+      fd_cols_add(c.a, SB_CONST(fdh_sp_add)[t]);
+      fd_cols_add(c.b, SB_CONST(fdh_sp_add)[t]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) c = fd_macc2(c, fd_todbl2(s[j]), &m[j][0]);
+      c = fd_macc2(c, x, &m[4][0]);
+      s[4] = fd_reduce2(c);
+    }
+#pragma unroll 1
+    for (int j = 0; j < 4; j++) {
+      fdc2 c = fd_cols_init2(1);
+      fd_cols_add_csub(c.a, s[j].a);
+      fd_cols_add_csub(c.b, s[j].b);
+      s[j] = fd_reduce2(fd_macc2(c, x, &m[5 + j][0]));
+    }
+  }
+  fdh_matmul2(s, SB_CONST(fdh_post), &SB_CONST(fdh_add)[25]);
+#pragma unroll 1
+  for (int r = 0; r < 4; r++) {
+#pragma unroll 1
+    for (int k = 0; k < 5; k++) s[k] = fd_pow5_2(s[k]);
+    fdh_matmul2(s, SB_CONST(fdh_mds), r < 3 ? &SB_CONST(fdh_add)[5 * (6 + r)] : nullptr);
+  }
+}
+
 // ---- memory-operand permutation: state and temporaries live in 8 slots (fd.cuh), stride `ls` between limbs -----
 // slots 0..4 = state words, 5..7 = S-box temporaries; slot j starts at base + j * 10 * ls doubles.
 constexpr int FDH_SLOTS = 8;
@@ -174,6 +239,19 @@ SB_HD void challenge3_fd(const fq& Ru, const fq& Rv, const fq& m, uint32_t* c) {
   fd s[5] = {fd_const_zero(), fd_from_fq(Ru), fd_from_fq(Rv), fd_from_fq(m), fd_const_one()};
   hades_perm_fd(s);
   fd_truncate250(s[1], c);
+}
+
+// two challenges at once: c[w] = H(Ru[w], Rv[w], m[w])
+SB_HD void challenge3_fd2(const fq* Ru, const fq* Rv, const fq* m, uint32_t (*c)[8]) {
+  fd2 s[5];
+  s[0] = {fd_const_zero(), fd_const_zero()};
+  s[1] = {fd_from_fq(Ru[0]), fd_from_fq(Ru[1])};
+  s[2] = {fd_from_fq(Rv[0]), fd_from_fq(Rv[1])};
+  s[3] = {fd_from_fq(m[0]), fd_from_fq(m[1])};
+  s[4] = {fd_const_one(), fd_const_one()};
+  hades_perm_fd2(s);
+  fd_truncate250(s[1].a, c[0]);
+  fd_truncate250(s[1].b, c[1]);
 }
 
 SB_HD void challenge3_fd_p(const fq& Ru, const fq& Rv, const fq& m, uint32_t* c, double* base, int ls) {

@@ -284,23 +284,24 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Warp-specialised single-key verification: one persistent 640-thread CTA per SM = 8 hash warps + 12 curve warps,
-// i.e. on every SM sub-partition (warp w runs on sub-partition w % 4) 2 hash warps beside 3 curve warps.
+// Warp-specialised single-key verification: one persistent 512-thread CTA per SM = 8 hash warps + 8 curve warps,
+// i.e. on every SM sub-partition (warp w runs on sub-partition w % 4) 2 hash warps beside 2 curve warps.
 //
 // The curve half of a verification (c*PK + u*G == R) saturates the FMA-heavy pipe with IMAD.WIDE while using ~40 %
 // of the issue slots; the Poseidon challenge on the FP64 pipe (hades_fd.cuh) needs issue slots and the FP64 / ALU
 // pipes only.  Keeping both kinds of warp on every sub-partition at all times overlaps the two: the hash warps
 // compute the challenges of the CTA's NEXT tile into shared memory while the curve warps verify the current tile.
-// A hash warp alone is latency-bound (IPC ~0.17 measured), hence two per sub-partition; the work per iteration is
-// 3 hashes per hash lane and 2 verifications per curve lane (tile = 12 x 32 x 2 = 8 x 32 x 3 = 768 tuples).
-// Tiles are handed out by a global counter; verdict words never straddle warps.
-// 96 registers per thread (20 warps per SM): the curve code measured within 2 % of its 128-register build.
+// Two curve warps per sub-partition already drive the FMA-heavy pipe to 94 % of what four do (measured with the
+// single-role kernel at 2 CTAs/SM), so the other two warp slots of the 128-register budget go to hash warps; a hash
+// warp alone is latency-bound (IPC ~0.17 measured), two per sub-partition keep up with one challenge per
+// verification.  Tile = 8 x 32 = 256 tuples per iteration, handed out by a global counter; verdict words never
+// straddle warps.
 // ------------------------------------------------------------------------------------------------
 #ifndef SB_VERIFY_WS
 #define SB_VERIFY_WS 1
 #endif
 #ifndef SB_WS_SETMAXNREG
-#define SB_WS_SETMAXNREG 1
+#define SB_WS_SETMAXNREG 0
 #endif
 #ifndef SB_WS_HREGS
 #define SB_WS_HREGS 56
@@ -308,9 +309,9 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
 #ifndef SB_WS_EREGS
 #define SB_WS_EREGS 120
 #endif
-constexpr int WS_HW = 8, WS_EW = 12, WS_THREADS = (WS_HW + WS_EW) * 32, WS_EPER = 2;
-constexpr int WS_TILE = WS_EW * 32 * WS_EPER;       // 768 tuples per iteration
-constexpr int WS_HPER = WS_TILE / (WS_HW * 32);     // 3 hashes per hash lane
+constexpr int WS_HW = 8, WS_EW = 8, WS_THREADS = (WS_HW + WS_EW) * 32, WS_EPER = 1;
+constexpr int WS_TILE = WS_EW * 32 * WS_EPER;       // 256 tuples per iteration
+constexpr int WS_HPER = WS_TILE / (WS_HW * 32);     // 1 hash per hash lane
 constexpr size_t WS_SMEM = (size_t)2 * WS_TILE * 8 * sizeof(uint32_t);
 static_assert(WS_HPER * WS_HW * 32 == WS_TILE, "hash and curve warps must cover the same tile");
 __global__ void __launch_bounds__(WS_THREADS, 1) k_verify_ws(const KArgs a) {
@@ -505,7 +506,7 @@ int launch(sb200_ctx* ctx, Op op, const KArgs& a, cudaStream_t st) {
   unsigned grid = (unsigned)((a.n + TPB - 1) / TPB);
   unsigned gridk = (unsigned)((a.n + TPB * SIGN_K - 1) / (TPB * SIGN_K));
 #if SB_VERIFY_WS
-  if (op == OP_VERIFY && a.n >= 2 * (int64_t)WS_TILE * a.nsm) {  // persistent warp-specialised kernel, one CTA per SM (small batches: k_run)
+  if (op == OP_VERIFY && (a.flags & SB200_VERIFY_DUAL_PIPE)) {  // persistent warp-specialised kernel, one CTA per SM
     CU(cudaMemsetAsync(&a.ws->tile, 0, sizeof(unsigned), st));
     unsigned ntiles = (unsigned)((a.n + WS_TILE - 1) / WS_TILE);
     unsigned g = std::min<unsigned>(ntiles, (unsigned)a.nsm);
@@ -532,7 +533,7 @@ int launch(sb200_ctx* ctx, Op op, const KArgs& a, cudaStream_t st) {
 
 int run(sb200_ctx* ctx, int64_t n, const Desc& d) {
   if (!ctx || n < 0) return SB200_ERR_ARG;
-  if (d.flags & ~(SB200_POINTS_AFFINE | SB200_DEVICE_PTRS)) return SB200_ERR_ARG;
+  if (d.flags & ~(SB200_POINTS_AFFINE | SB200_DEVICE_PTRS | (d.op == OP_VERIFY ? SB200_VERIFY_DUAL_PIPE : 0u))) return SB200_ERR_ARG;
   for (int k = 0; k < d.nin; k++)
     if (d.in_words[k] && (!d.in[k] || ((uintptr_t)d.in[k] & 15))) return SB200_ERR_ARG;
   for (int k = 0; k < d.nout; k++)

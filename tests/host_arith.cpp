@@ -50,6 +50,10 @@ void h_challenge3(const uint32_t* ru, const uint32_t* rv, const uint32_t* m, int
   else if (fdpath == 3) challenge3_fd_p(L(ru), L(rv), L(m), c, slots + 1, 3);  // strided layout
   else if (fdpath) challenge3_fd(L(ru), L(rv), L(m), c); else challenge3(L(ru), L(rv), L(m), c);
 }
+void h_challenge3_pair(const uint32_t* ru, const uint32_t* rv, const uint32_t* m, uint32_t* c) {  // 2 x (8 words) each
+  fq a[2] = {L(ru), L(ru + 8)}, b[2] = {L(rv), L(rv + 8)}, mm[2] = {L(m), L(m + 8)};
+  challenge3_fd2(a, b, mm, reinterpret_cast<uint32_t(*)[8]>(c));
+}
 void h_challenge5(const uint32_t* ru, const uint32_t* rv, const uint32_t* rpu, const uint32_t* rpv, const uint32_t* m, int fdpath, uint32_t* c) {
   if (fdpath) challenge5_fd(L(ru), L(rv), L(rpu), L(rpv), L(m), c); else challenge5(L(ru), L(rv), L(rpu), L(rpv), L(m), c);
 }

@@ -140,6 +140,12 @@ def test_config1_single_verify_2_16_vs_cpu_restatement(engine):
     u, R_, c = engine.sign(sk, msg, nonce)
     ok, c2 = engine.verify(pk, u, R_, msg)
     assert ok.all() and (c2 == c).all()
+    # the warp-specialised (dual-pipe) kernel: same verdicts and challenges, also with 10 % corrupted signatures
+    bad = u.copy()
+    bad[::10, 0] ^= 1
+    ok_a, c_a = engine.verify(pk, bad, R_, msg)
+    ok_b, c_b = engine.verify(pk, bad, R_, msg, dual_pipe=True)
+    assert (ok_a == ok_b).all() and (c_a == c_b).all() and not ok_b[::10].any() and ok_b[1::10].all()
     okc, cc = ref_cpu.verify(pk[:4096], u[:4096], R_[:4096], msg[:4096])
     assert okc.all() and (cc == c[:4096]).all()
     uc, Rc, _ = ref_cpu.sign(sk[:2048], msg[:2048], nonce[:2048])

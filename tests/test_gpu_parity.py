@@ -142,10 +142,11 @@ def corrupt_single(rnd, i, pk, u, Rp, m, pks):
     return pk, u, Rp, m
 
 
+@pytest.mark.parametrize("dual_pipe", [False, True], ids=["single-role", "dual-pipe"])
 @pytest.mark.parametrize("affine", [True, False])
-def test_verify_single(engine, affine):
+def test_verify_single(engine, affine, dual_pipe):
     rnd = random.Random(19)
-    n = 257  # ragged: not a multiple of 32
+    n = 257 + (256 if dual_pipe else 0)  # ragged: not a multiple of 32 (dual-pipe: more than one 256-tuple tile)
     sk, nonce, m = make_single(rnd, n)
     pks = [V.mul(o.G, a) for a in sk]
     sigs = [o.sign(a, b, mm, mul=V.mul) for a, b, mm in zip(sk, nonce, m)]
@@ -158,7 +159,7 @@ def test_verify_single(engine, affine):
     zs1 = None if affine else [rnd.randrange(1, Q) for _ in tup]
     zs2 = None if affine else [rnd.randrange(1, Q) for _ in tup]
     ok, c = engine.verify(V.points([t[0] for t in tup], zs1), V.scalars([t[1] for t in tup]),
-                          V.points([t[2] for t in tup], zs2), V.fqs([t[3] for t in tup]), affine=affine)
+                          V.points([t[2] for t in tup], zs2), V.fqs([t[3] for t in tup]), affine=affine, dual_pipe=dual_pipe)
     assert list(ok) == exp
     assert V.ints_out(c) == [o.challenge_hash(t[2], t[3]) for t in tup]
 

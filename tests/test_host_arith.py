@@ -230,3 +230,16 @@ def test_challenge_fd_matches_imad_path_and_oracle(lib):
         args = [H.ptr(H.mont(P1[0])), H.ptr(H.mont(P1[1])), H.ptr(H.mont(P2[0])), H.ptr(H.mont(P2[1])), H.ptr(H.mont(m))]
         lib.h_challenge5(*args, 0, H.ptr(c0)); lib.h_challenge5(*args, 1, H.ptr(c1))
         assert H.to_int(c0) == H.to_int(c1) == o.challenge_hash_double(P1, P2, m)
+
+
+def test_challenge_fd_pair(lib):
+    """two interleaved permutations per call (the hash warps of the warp-specialised verify kernel)"""
+    rnd = random.Random(15)
+    out = np.zeros(16, np.uint32)
+    for _ in range(4):
+        P = [V.mul(o.G, rnd.randrange(R)) for _ in range(2)]
+        m = [rnd.randrange(Q), rnd.choice([0, Q - 1])]
+        ru = np.concatenate([H.mont(p[0]) for p in P]); rv = np.concatenate([H.mont(p[1]) for p in P])
+        mm = np.concatenate([H.mont(x) for x in m])
+        lib.h_challenge3_pair(H.ptr(ru), H.ptr(rv), H.ptr(mm), H.ptr(out))
+        assert [H.to_int(out[:8]), H.to_int(out[8:])] == [o.challenge_hash(P[0], m[0]), o.challenge_hash(P[1], m[1])]

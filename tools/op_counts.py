@@ -43,7 +43,7 @@ buf = np.zeros(8, np.uint32)
 
 def measure(fn):
     lib.h_counts_reset(); fn(); lib.h_counts_get(H.ptr(cnt))
-    w, mul, sqr, addsub, frm, dot5 = (int(x) for x in cnt)
+    w, mul, sqr, addsub, frm, dot5 = (int(x) for x in cnt[:6])
     return {"imad_wide_per_tuple": w, "fq_mul": mul, "fq_sqr": sqr, "fq_dot5": dot5, "fq_addsub": addsub, "fr_mont_mul": frm}
 
 out = {}
