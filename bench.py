@@ -59,7 +59,7 @@ def corrupt_mask(n):
 class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.power = index, [], set(), False, None, []
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -80,6 +80,7 @@ class ClockSampler(threading.Thread):
         while not self.stop_flag:
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 for k, v in names.items():
                     bit = getattr(nv, "nvmlClocksThrottleReason" + k, 0)
@@ -92,7 +93,18 @@ class ClockSampler(threading.Thread):
     def result(self):
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(x for x in self.reasons if x != "gpu_idle"), "samples": len(s)}
+                "reasons": sorted(x for x in self.reasons if x != "gpu_idle"), "samples": len(s),
+                "power_w_max": max(self.power) if self.power else None}
+
+
+def ncu_traffic(n):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the verify kernel from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py), scaled to this launch's tuple count; None if absent."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["verify_affine"]
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) * n / t["tuples"]
+    except Exception:
+        return None
 
 
 def cpu_reference_arm(args):
@@ -146,7 +158,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from schnorr_b200 import DEVICE_PTRS, POINTS_AFFINE, Engine
+    from schnorr_b200 import DEVICE_PTRS, POINTS_AFFINE, VERIFY_DUAL_PIPE, Engine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -237,7 +249,7 @@ def main():
         wide = ops["imad_wide_per_tuple"]
         achieved = n * wide / (ms_step * 1e-3) / 1e12
         roof = {"bound": "imad", "achieved": achieved, "peak": peak["imad_wide_per_s"] / 1e12, "unit": "T IMAD.WIDE/s",
-                "frac": achieved / (peak["imad_wide_per_s"] / 1e12), "traffic": ops.get("dram_bytes_per_launch_ncu"),
+                "frac": achieved / (peak["imad_wide_per_s"] / 1e12), "traffic": ncu_traffic(n),
                 "peak_source": "IMAD_PEAK.json (tools/imad_peak.cu measured on this pool's B200: IMAD.WIDE carry-chain issue rate)",
                 "work": f"{wide} IMAD.WIDE.U32 per verification ({ops['fq_mul']} fq_mul, {ops['fq_sqr']} fq_sqr, {ops.get('fq_dot5', 0)} fq_dot5)",
                 "hbm": {"achieved_gbs": (h2d + d2h) / (ms_step * 1e-3) / 1e9,
@@ -271,6 +283,7 @@ def main():
         extras["sign_double_per_s"] = timed(lambda: eng.call("sign_double", ne, fl, P(d_sk), P(d_msg), P(d_nonce), P(d_uo), P(d_Ro), P(d_Ro2), P(d_co)))
         extras["verify_double_per_s"] = timed(lambda: eng.call("verify_double", ne, fl, P(d_pk), P(d_pk), P(d_u), P(d_R), P(d_R), P(d_msg), P(d_bm), None))
         extras["verify_vargen_per_s"] = timed(lambda: eng.call("verify_vargen", ne, fl, P(d_pk), P(d_pk), P(d_u), P(d_R), P(d_msg), P(d_bm), None))
+        extras["verify_dual_pipe_per_s"] = timed(lambda: eng.call("verify", ne, fl | VERIFY_DUAL_PIPE, P(d_pk), P(d_u), P(d_R), P(d_msg), P(d_bm), None))
         extras["keygen_per_s"] = timed(lambda: eng.call("keygen", ne, fl, P(d_sk), P(d_Ro)))
         extras["batch"] = ne
         extras["note"] = "device-resident, CUDA events, per-op kernels of the same library; verdict content not checked here"

@@ -67,28 +67,44 @@ SB_HD ext ext_identity() {
 template <bool INL = false>
 SB_HD proj p1p1_to_proj(const p1p1& c) {
   proj r;
-  r.X = mulT<INL>(c.E, c.F);
-  r.Y = mulT<INL>(c.G, c.H);
+  if (INL) {
+    r.X = fq_mul_inl(c.E, c.F);
+    r.Y = fq_mul_inl(c.G, c.H);
+  } else {
+    fq_mul2(c.E, c.F, c.G, c.H, r.X, r.Y);
+  }
   r.Z = mulT<INL>(c.F, c.G);
   return r;
 }
 template <bool INL = false>
 SB_HD ext p1p1_to_ext(const p1p1& c) {
   ext r;
-  r.X = mulT<INL>(c.E, c.F);
-  r.Y = mulT<INL>(c.G, c.H);
-  r.Z = mulT<INL>(c.F, c.G);
-  r.T = mulT<INL>(c.E, c.H);
+  if (INL) {
+    r.X = fq_mul_inl(c.E, c.F);
+    r.Y = fq_mul_inl(c.G, c.H);
+    r.Z = fq_mul_inl(c.F, c.G);
+    r.T = fq_mul_inl(c.E, c.H);
+  } else {
+    fq_mul2(c.E, c.F, c.G, c.H, r.X, r.Y);
+    fq_mul2(c.F, c.G, c.E, c.H, r.Z, r.T);
+  }
   return r;
 }
 
 // 2P, 4 squarings (dbl-2008-hwcd with a = -1, signs arranged so H = A + B, F = C - G)
 template <bool INL = false>
 SB_HD p1p1 ed_dbl(const fq& X, const fq& Y, const fq& Z) {
-  fq A = sqrT<INL>(X);
-  fq B = sqrT<INL>(Y);
-  fq C = fq_dbl(sqrT<INL>(Z));
-  fq S = sqrT<INL>(fq_add(X, Y));
+  fq A, B, C, S;
+  if (INL) {
+    A = fq_sqr_inl(X);
+    B = fq_sqr_inl(Y);
+    C = fq_sqr_inl(Z);
+    S = fq_sqr_inl(fq_add(X, Y));
+  } else {
+    fq_sqr2(X, Y, A, B);
+    fq_sqr2(Z, fq_add(X, Y), C, S);
+  }
+  C = fq_dbl(C);
   p1p1 r;
   r.H = fq_add(A, B);
   r.G = fq_sub(B, A);
@@ -100,10 +116,17 @@ SB_HD p1p1 ed_dbl(const fq& X, const fq& Y, const fq& Z) {
 // P + Q, Q in projective Niels form: 4 multiplications (add-2008-hwcd-3, k = 2d)
 template <bool INL = false>
 SB_HD p1p1 ed_add(const ext& p, const pniels& q) {
-  fq A = mulT<INL>(fq_sub(p.Y, p.X), q.YmX);
-  fq B = mulT<INL>(fq_add(p.Y, p.X), q.YpX);
-  fq C = mulT<INL>(p.T, q.T2d);
-  fq D = fq_dbl(mulT<INL>(p.Z, q.Z));
+  fq A, B, C, D;
+  if (INL) {
+    A = fq_mul_inl(fq_sub(p.Y, p.X), q.YmX);
+    B = fq_mul_inl(fq_add(p.Y, p.X), q.YpX);
+    C = fq_mul_inl(p.T, q.T2d);
+    D = fq_mul_inl(p.Z, q.Z);
+  } else {
+    fq_mul2(fq_sub(p.Y, p.X), q.YmX, fq_add(p.Y, p.X), q.YpX, A, B);
+    fq_mul2(p.T, q.T2d, p.Z, q.Z, C, D);
+  }
+  D = fq_dbl(D);
   p1p1 r;
   r.E = fq_sub(B, A);
   r.F = fq_sub(D, C);
@@ -115,8 +138,13 @@ SB_HD p1p1 ed_add(const ext& p, const pniels& q) {
 // P + Q, Q affine Niels: 3 multiplications
 template <bool INL = false>
 SB_HD p1p1 ed_add(const ext& p, const aniels& q) {
-  fq A = mulT<INL>(fq_sub(p.Y, p.X), q.YmX);
-  fq B = mulT<INL>(fq_add(p.Y, p.X), q.YpX);
+  fq A, B;
+  if (INL) {
+    A = fq_mul_inl(fq_sub(p.Y, p.X), q.YmX);
+    B = fq_mul_inl(fq_add(p.Y, p.X), q.YpX);
+  } else {
+    fq_mul2(fq_sub(p.Y, p.X), q.YmX, fq_add(p.Y, p.X), q.YpX, A, B);
+  }
   fq C = mulT<INL>(p.T, q.T2d);
   fq D = fq_dbl(p.Z);
   p1p1 r;
@@ -239,6 +267,9 @@ SB_HD p1p1 pt_dbl(const p1p1& c) {
 #endif
 }
 
+#ifndef SB_DBL_ROLL
+#define SB_DBL_ROLL 4  // how many of the 4 doublings per window run as a rolled loop
+#endif
 SB_HD pniels vartable_lookup(const pniels* tab, int d) {
   bool neg = d < 0;
   int idx = neg ? -d : d;
@@ -250,10 +281,14 @@ SB_HD p1p1 ed_mul_var(const pniels* tab, const uint32_t* k_rec, int nwin) {
   p1p1 c = ed_add(ext_identity(), vartable_lookup(tab, recode_digit<4>(k_rec, nwin - 1)));
 #pragma unroll 1
   for (int i = nwin - 2; i >= 0; i--) {
-    c = pt_dbl(c);
-    c = pt_dbl(c);
-    c = pt_dbl(c);
-    c = pt_dbl(c);
+    // rolled: four copies of the doubling's call sequence make the loop body 25 KB, and together with the
+    // multiplier bodies it no longer fits the 32 KB L1.5 instruction cache (ncu: stall_no_instruction 1.3 per issue)
+#pragma unroll 1
+    for (int k = 0; k < SB_DBL_ROLL; k++) c = pt_dbl(c);
+#if SB_DBL_ROLL < 4
+#pragma unroll
+    for (int k = SB_DBL_ROLL; k < 4; k++) c = pt_dbl(c);
+#endif
     ext e = p1p1_to_ext(c);
     c = ed_add(e, vartable_lookup(tab, recode_digit<4>(k_rec, i)));
   }
@@ -267,10 +302,14 @@ SB_HD p1p1 ed_mul_var2(const pniels* tab1, const uint32_t* k1_rec, const pniels*
   c = ed_add(p1p1_to_ext(c), vartable_lookup(tab2, recode_digit<4>(k2_rec, nwin - 1)));
 #pragma unroll 1
   for (int i = nwin - 2; i >= 0; i--) {
-    c = pt_dbl(c);
-    c = pt_dbl(c);
-    c = pt_dbl(c);
-    c = pt_dbl(c);
+    // rolled: four copies of the doubling's call sequence make the loop body 25 KB, and together with the
+    // multiplier bodies it no longer fits the 32 KB L1.5 instruction cache (ncu: stall_no_instruction 1.3 per issue)
+#pragma unroll 1
+    for (int k = 0; k < SB_DBL_ROLL; k++) c = pt_dbl(c);
+#if SB_DBL_ROLL < 4
+#pragma unroll
+    for (int k = SB_DBL_ROLL; k < 4; k++) c = pt_dbl(c);
+#endif
     ext e = p1p1_to_ext(c);
     c = ed_add(e, vartable_lookup(tab1, recode_digit<4>(k1_rec, i)));
     e = p1p1_to_ext(c);
