@@ -63,7 +63,7 @@ enum {
  * the stream set with sb200_set_stream and returns without synchronising. */
 #define SB200_DEVICE_PTRS 2u
 /* sb200_verify only: run the warp-specialised kernel (hash warps on the FP64 pipe beside curve warps on the
- * FMA-heavy pipe, DESIGN.md 4.5).  Same verdicts and challenges; measured at parity with the default kernel. */
+ * FMA-heavy pipe, DESIGN.md 4.4).  Same verdicts and challenges; measured at parity with the default kernel. */
 #define SB200_VERIFY_DUAL_PIPE 4u
 
 /* devices: CUDA ordinals to shard over (tuples are split into contiguous blocks, multiples of 32);

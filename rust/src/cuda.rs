@@ -30,6 +30,8 @@ pub struct Sb200Ctx {
 pub const SB200_POINTS_PROJECTIVE: u32 = 0;
 pub const SB200_POINTS_AFFINE: u32 = 1;
 pub const SB200_DEVICE_PTRS: u32 = 2;
+/// `sb200_verify` only: warp-specialised kernel (hash warps on the FP64 pipe beside curve warps); same results.
+pub const SB200_VERIFY_DUAL_PIPE: u32 = 4;
 
 #[link(name = "schnorr_b200")]
 extern "C" {
