@@ -128,6 +128,9 @@ SB_HD bool verify_vargen_core(const point_in& PK, const point_in& GEN, const uin
   return ok & p1p1_equals(cp, R);
 }
 
+#ifndef SB_DOUBLE_ROLL
+#define SB_DOUBLE_ROLL 1
+#endif
 SB_HD bool verify_double_core(const point_in& PK, const point_in& PKp, const uint32_t* u_in, const point_in& R,
                               const point_in& Rp, const fq& m, const uint32_t* combG, const uint32_t* combGp,
                               uint32_t* c_out) {
@@ -151,6 +154,20 @@ SB_HD bool verify_double_core(const point_in& PK, const point_in& PKp, const uin
   for (int i = 0; i < 8; i++) u[i] = ok ? u_in[i] : 0u;
   recode_offset<4>(c);
   recode_offset<COMB_BITS>(u);
+#if SB_DOUBLE_ROLL
+  // the two key / nonce-point pairs run through ONE copy of the curve code (a 2-trip loop): two inlined copies double
+  // the hot code and warps in different halves evict each other from the instruction cache
+#pragma unroll 1
+  for (int k = 0; k < 2; k++) {
+    const point_in& key = k ? PKp : PK;
+    const point_in& rr = k ? Rp : R;
+    pniels tab[9];
+    vartable_build(tab, point_to_ext(key));
+    p1p1 cp = ed_mul_var(tab, c, 63);
+    cp = ed_comb_add(p1p1_to_ext(cp), k ? combGp : combG, u);
+    ok &= p1p1_equals(cp, rr);
+  }
+#else
   pniels tab[9];
   vartable_build(tab, point_to_ext(PK));
   p1p1 cp = ed_mul_var(tab, c, 63);
@@ -160,6 +177,7 @@ SB_HD bool verify_double_core(const point_in& PK, const point_in& PKp, const uin
   cp = ed_mul_var(tab, c, 63);
   cp = ed_comb_add(p1p1_to_ext(cp), combGp, u);
   ok &= p1p1_equals(cp, Rp);
+#endif
   return ok;
 }
 
