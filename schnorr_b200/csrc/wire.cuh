@@ -75,6 +75,47 @@ SB_HD bool fq_sqrt(const fq& x, fq& root) {
   return ok;
 }
 
+// sqrt(num / den) without an inversion and without the Tonelli-Shanks search loops (den != 0):
+//   y = num den,  a = y^(-(t+1)/2) (one 255-bit exponentiation),  b = a^2 y = y^-t lies in the subgroup of order 2^32 = <g>;
+//   the discrete logarithm k of b (b = g^k) is read off in eight 4-bit digits, Pohlig-Hellman style -- digit i is
+//   the position of (b g^-(k mod 16^i))^(2^(28-4i)) among the 16 sixteenth roots of unity W[] -- and then
+//   sqrt(1/y) = a g^(-k/2), sqrt(num/den) = num sqrt(1/y).  112 squarings + 16 multiplications replace ~500 squarings
+//   of the bit-serial search (whose trip counts also diverge across the lanes of a warp), and the separate field
+//   inversion (255 squarings) disappears: 2.6x fewer multiplications per decompressed point.
+// Branch-free; a non-residue (odd k) or garbage input yields a wrong candidate that the closing check u^2 den == num
+// rejects, so the function is self-verifying.  Returns the candidate in `u` (either root; the caller fixes the sign).
+#ifndef SB_FAST_DECOMPRESS
+#define SB_FAST_DECOMPRESS 1
+#endif
+#if defined(__CUDACC__)
+__device__ const uint32_t d_fq_dlog_w[16][8] = SB200_FQ_DLOG_W_INIT;
+__device__ const uint32_t d_fq_dlog_p[128][8] = SB200_FQ_DLOG_P_INIT;
+__device__ const uint32_t d_fq_dlog_q[128][8] = SB200_FQ_DLOG_Q_INIT;
+#endif
+static const uint32_t h_fq_dlog_w[16][8] = SB200_FQ_DLOG_W_INIT;
+static const uint32_t h_fq_dlog_p[128][8] = SB200_FQ_DLOG_P_INIT;
+static const uint32_t h_fq_dlog_q[128][8] = SB200_FQ_DLOG_Q_INIT;
+
+SB_HD bool fq_sqrt_ratio(const fq& num, const fq& den, fq& u) {
+  const uint32_t e[8] = SB200_FQ_ISQRT_EXP_INIT;
+  fq y = fq_mul(num, den);
+  fq a = fq_pow_const(y, e, SB200_FQ_ISQRT_EXP_BITS);  // y^(-(t+1)/2)
+  fq b = fq_mul(fq_sqr(a), y);                          // y^-t
+#pragma unroll 1
+  for (int i = 0; i < 8; i++) {
+    fq h = b;
+#pragma unroll 1
+    for (int s = 0; s < 28 - 4 * i; s++) h = fq_sqr(h);
+    int d = 0;
+#pragma unroll 1
+    for (int j = 1; j < 16; j++) d = fq_eq(h, ld8(SB_CONST(fq_dlog_w)[j])) ? j : d;
+    b = fq_mul(b, ld8(SB_CONST(fq_dlog_p)[16 * i + d]));
+    a = fq_mul(a, ld8(SB_CONST(fq_dlog_q)[16 * i + d]));
+  }
+  u = fq_mul(num, a);
+  return fq_eq(fq_mul(fq_sqr(u), den), num);
+}
+
 // 32 bytes (as 8 LE words) -> affine point, Montgomery.  false <=> the reference's from_bytes returns None.
 SB_HD bool point_decompress(const uint32_t* in, fq& u, fq& v) {
   uint32_t vb[8];
@@ -90,8 +131,12 @@ SB_HD bool point_decompress(const uint32_t* in, fq& u, fq& v) {
   fq v2 = fq_sqr(v);
   fq num = fq_sub(v2, fq_one());
   fq den = fq_add(fq_one(), fq_mul(ed_d(), v2));
+#if SB_FAST_DECOMPRESS
+  ok &= fq_sqrt_ratio(num, den, u);  // den = 1 + d v^2 != 0: d is a non-square, -1 a square
+#else
   fq x = fq_mul(num, fq_inv(den));  // den = 0 -> inverse "0" -> x = 0, as invert().unwrap_or(zero)
   ok &= fq_sqrt(x, u);
+#endif
   uint32_t parity = fq_from_mont(u).v[0] & 1u;
   u = fq_select(u, fq_neg(u), parity != sign);
   return ok;

@@ -95,6 +95,7 @@ int h_decompress(const uint32_t* b, uint32_t* uv) { fq u, v; bool ok = point_dec
 void h_compress(const uint32_t* uv, uint32_t* b) { point_compress(L(uv), L(uv + 8), b); }
 void h_fr_from_wide(const uint32_t* w, uint32_t* r) { fr_from_wide(w, r); }
 void h_fq_from_wide(const uint32_t* w, uint32_t* r) { S(r, fq_from_wide(w)); }
+int h_fq_sqrt_ratio(const uint32_t* n, const uint32_t* d, uint32_t* r) { fq x; bool ok = fq_sqrt_ratio(L(n), L(d), x); S(r, x); return ok; }
 int h_fq_sqrt(const uint32_t* a, uint32_t* r) { fq x; bool ok = fq_sqrt(L(a), x); S(r, x); return ok; }
 int h_verify_bytes(const uint32_t* pk, const uint32_t* sig, const uint32_t* msg, const uint32_t* combG, int* invalid) {
   bool inv; bool ok = verify_bytes_core(pk, sig, msg, combG, inv); *invalid = inv; return ok;

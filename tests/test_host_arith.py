@@ -127,6 +127,17 @@ def test_wire_formats(lib, tabs):
         assert bool(ok) == is_sq
         if is_sq:
             assert pow(H.unmont(out), 2, Q) == x
+    # sqrt(num / den) by one exponentiation + table-driven discrete log: residues of every 2-power order class
+    # (x = g^j z^2 ... covered by random x and by x with x^t of maximal order), non-residues, num = 0
+    g = pow(7, (Q - 1) >> 32, Q)
+    specials = [(0, 5), (1, 1), (4, 1), (1, 4), (Q - 1, 1), (g, 1), (pow(g, 2, Q), 1), (pow(g, 1 << 31, Q), 1), (pow(g, 6, Q), 9)]
+    for n, d in specials + [(rnd.randrange(Q), rnd.randrange(1, Q)) for _ in range(60)]:
+        ok = lib.h_fq_sqrt_ratio(H.ptr(H.mont(n)), H.ptr(H.mont(d)), H.ptr(out))
+        x = n * pow(d, -1, Q) % Q
+        is_sq = x == 0 or pow(x, (Q - 1) // 2, Q) == 1
+        assert bool(ok) == is_sq, (n, d)
+        if is_sq:
+            assert pow(H.unmont(out), 2, Q) == x
     # decompress / compress
     pts = V.torsion_points() + [o.G, o.G_NUMS] + [V.rand_curve_point(rnd) for _ in range(10)]
     for P in pts:

@@ -264,6 +264,30 @@ def main():
     w("#define SB200_FQ_ROOT_OF_UNITY_INIT %s" % fmt(mont(g_root)))
     w("#define SB200_FQ_SQRT_EXP_INIT %s   // (t - 1) / 2, plain integer" % fmt((t_odd - 1) // 2))
     w("#define SB200_FQ_SQRT_EXP_BITS %d" % ((t_odd - 1) // 2).bit_length())
+    # Inverse square root with a table-driven discrete logarithm in the 2^32-order subgroup (csrc/wire.cuh):
+    #   y^(-(t+1)/2) by one exponentiation, then Pohlig-Hellman over eight 4-bit digits of k where y^-t = g^k.
+    isqrt_exp = (Q - 1) - (t_odd + 1) // 2
+    assert pow(5, isqrt_exp, Q) == pow(pow(5, (t_odd + 1) // 2, Q), -1, Q)
+    w("// y^ISQRT_EXP = y^(-(t+1)/2); digit tables: W[d] = g^(d 2^28), P[i][d] = g^(-d 16^i), Q[i][d] = g^(-d 16^i / 2)")
+    w("#define SB200_FQ_ISQRT_EXP_INIT %s   // q - 1 - (t + 1)/2, plain integer" % fmt(isqrt_exp))
+    w("#define SB200_FQ_ISQRT_EXP_BITS %d" % isqrt_exp.bit_length())
+    omega = pow(g_root, 1 << 28, Q)
+    ginv = pow(g_root, -1, Q)
+    w("#define SB200_FQ_DLOG_W_INIT { \\")
+    for d in range(16):
+        w("  %s, \\" % fmt(mont(pow(omega, d, Q))))
+    w("}")
+    w("#define SB200_FQ_DLOG_P_INIT { \\")
+    for i in range(8):
+        for d in range(16):
+            w("  %s, \\" % fmt(mont(pow(ginv, d * 16 ** i, Q))))
+    w("}")
+    w("#define SB200_FQ_DLOG_Q_INIT { \\")
+    for i in range(8):
+        for d in range(16):
+            ex = d * 16 ** i
+            w("  %s, \\" % fmt(mont(pow(ginv, ex // 2, Q) if ex % 2 == 0 else 1)))  # odd total exponent: non-residue, caught by the final check
+    w("}")
     w("// Hades252: WIDTH 5, 8 full + 59 partial rounds; round keys = SHA-512 chain over \"poseidon-for-plonk\"")
     w("// (dusk-hades ark.bin), first 335 of 960; MDS[i][j] = 1/(i + j + 5) (dusk-hades mds.bin).")
     w("#define SB200_HADES_NRC %d" % ((FULL + PARTIAL) * WIDTH))
