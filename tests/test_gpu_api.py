@@ -153,6 +153,33 @@ def test_config1_single_verify_2_16_vs_cpu_restatement(engine):
     assert (ref_cpu.keygen(sk[:2048]) == pk[:2048]).all()
 
 
+@pytest.mark.parametrize("dual_pipe", [False, True], ids=["single-role", "dual-pipe"])
+def test_ragged_batch_across_pipeline_chunks(engine, dual_pipe):
+    """n = 2^18 + 33: the host-buffer path splits it into a full 2^18 chunk and a 33-tuple tail on the second stream;
+    verdict words, challenge rows and the projective (Z != 1) path must line up across the chunk boundary"""
+    n = (1 << 18) + 33
+    sk, nonce, msg = _synth(n, 0xC5)
+    pk = engine.keygen(sk)
+    u, R_, c = engine.sign(sk, msg, nonce)
+    bad = (np.arange(n) % 7) == 3
+    u[bad, 0] ^= 1
+    ok, c2 = engine.verify(pk, u, R_, msg, dual_pipe=dual_pipe)
+    assert (ok == ~bad).all() and (c2 == c).all()
+    # the same points as (U : V : Z) with a per-tuple Z: multiply by z = 2 (Montgomery limbs of 2, 4 ...) on the host
+    m = 4096  # a slice that straddles nothing special; projective inputs cost an inversion each
+    z = np.array([(2 + i % 5) for i in range(m)], dtype=object)
+    Q = o.Q
+    def scale(pts):
+        out = np.zeros((m, 24), np.uint32)
+        for i in range(m):
+            x, y = V.unmont(pts[i, :8]), V.unmont(pts[i, 8:])
+            out[i] = np.concatenate([V.mont(x * z[i] % Q), V.mont(y * z[i] % Q), V.mont(int(z[i]))])
+        return out
+    s0 = n - m
+    okp, cp = engine.verify(scale(pk[s0:]), u[s0:], scale(R_[s0:]), msg[s0:], affine=False, dual_pipe=dual_pipe)
+    assert (okp == ok[s0:]).all() and (cp == c[s0:]).all()
+
+
 def test_config2_double_verify_2_20_properties(engine):
     n = 1 << 20
     sk, nonce, msg = _synth(n, 0xC2)
