@@ -22,7 +22,7 @@ fl = POINTS_AFFINE | DEVICE_PTRS
 vfl = fl | (4 if os.environ.get("SB_DUAL") else 0)  # SB200_VERIFY_DUAL_PIPE
 P = lambda x: x.data_ptr()
 calls = {
-  "verify": lambda: e.call("verify", n, vfl, P(d_pk), P(d_u), P(d_R), P(d_msg), P(bm), None),
+  "verify": lambda: e.call("verify", n, vfl, P(d_pk), P(d_u), P(d_R), P(d_msg), P(bm), P(co) if os.environ.get("SB_COUT") else None),
   "verify_vargen": lambda: e.call("verify_vargen", n, fl, P(d_pk), P(d_pk), P(d_u), P(d_R), P(d_msg), P(bm), None),
   "verify_double": lambda: e.call("verify_double", n, fl, P(d_pk), P(d_pk), P(d_u), P(d_R), P(d_R), P(d_msg), P(bm), None),
   "sign": lambda: e.call("sign", n, fl, P(d_sk), P(d_msg), P(d_nonce), P(uo), P(Ro), P(co)),
