@@ -132,6 +132,23 @@ int sb200_verify_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t*
 int sb200_sign_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* sk32, const uint8_t* msg32,
                      const uint8_t* nonce32, uint8_t* sig64_out);
 
+/* The same for the other two schemes:
+ * pk64  = PublicKeyDouble::to_bytes = pk || pk'           /root/reference/src/keys/public.rs:282-299
+ *       | PublicKeyVarGen::to_bytes = pk || generator     /root/reference/src/keys/public.rs:347-372
+ * sig96 = SignatureDouble::to_bytes = u || R || R'        /root/reference/src/signatures.rs:245-270
+ * sig64 = SignatureVarGen::to_bytes = u || R              /root/reference/src/signatures.rs:387-404
+ * sk64  = SecretKeyVarGen::to_bytes = sk || generator     /root/reference/src/keys/secret.rs:313-336 */
+int sb200_verify_double_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* pk64, const uint8_t* sig96,
+                              const uint8_t* msg32, uint32_t* verdicts, uint32_t* invalid);
+int sb200_verify_vargen_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* pk64, const uint8_t* sig64,
+                              const uint8_t* msg32, uint32_t* verdicts, uint32_t* invalid);
+/* SecretKey::from_bytes(sk).sign_double(nonce, msg).to_bytes() */
+int sb200_sign_double_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* sk32, const uint8_t* msg32,
+                            const uint8_t* nonce32, uint8_t* sig96_out);
+/* SecretKeyVarGen::from_bytes(sk64)?.sign(nonce, msg).to_bytes(); ok bit i = 0 where the generator does not decode */
+int sb200_sign_vargen_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* sk64, const uint8_t* msg32,
+                            const uint8_t* nonce32, uint8_t* sig64_out, uint32_t* ok_bitmap);
+
 /* Building-block probes for the parity tests (same kernels' device functions, one element per thread).
  * op: 0 mul (Montgomery product), 1 add, 2 sub, 3 inverse (b ignored), 4 square, 5 to_mont, 6 from_mont */
 int sb200_dbg_fq(sb200_ctx* ctx, int64_t n, int op, const uint32_t* a, const uint32_t* b, uint32_t* out);

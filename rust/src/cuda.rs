@@ -74,6 +74,16 @@ extern "C" {
                           verdicts: *mut u32, invalid: *mut u32) -> c_int;
     fn sb200_sign_bytes(ctx: *mut Sb200Ctx, n: i64, flags: u32, sk32: *const u8, msg32: *const u8, nonce32: *const u8,
                         sig64_out: *mut u8) -> c_int;
+    // the double-key and variable-generator schemes in their `Serializable` forms
+    // (pk64 = pk || pk' | pk || generator; sig96 = u || R || R'; sk64 = sk || generator)
+    fn sb200_verify_double_bytes(ctx: *mut Sb200Ctx, n: i64, flags: u32, pk64: *const u8, sig96: *const u8,
+                                 msg32: *const u8, verdicts: *mut u32, invalid: *mut u32) -> c_int;
+    fn sb200_verify_vargen_bytes(ctx: *mut Sb200Ctx, n: i64, flags: u32, pk64: *const u8, sig64: *const u8,
+                                 msg32: *const u8, verdicts: *mut u32, invalid: *mut u32) -> c_int;
+    fn sb200_sign_double_bytes(ctx: *mut Sb200Ctx, n: i64, flags: u32, sk32: *const u8, msg32: *const u8,
+                               nonce32: *const u8, sig96_out: *mut u8) -> c_int;
+    fn sb200_sign_vargen_bytes(ctx: *mut Sb200Ctx, n: i64, flags: u32, sk64: *const u8, msg32: *const u8,
+                               nonce32: *const u8, sig64_out: *mut u8, ok_bitmap: *mut u32) -> c_int;
 }
 
 /// Owns one `sb200_ctx` (comb tables of G and G' resident on each listed device).  There is no CPU

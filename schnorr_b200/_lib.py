@@ -63,6 +63,10 @@ def load_library() -> ctypes.CDLL:
         "sb200_fq_from_mont": (ci, [vp, i64, u32] + [u32p] * 2),
         "sb200_verify_bytes": (ci, [vp, i64, u32] + [u32p] * 5),
         "sb200_sign_bytes": (ci, [vp, i64, u32] + [u32p] * 4),
+        "sb200_verify_double_bytes": (ci, [vp, i64, u32] + [u32p] * 5),
+        "sb200_verify_vargen_bytes": (ci, [vp, i64, u32] + [u32p] * 5),
+        "sb200_sign_double_bytes": (ci, [vp, i64, u32] + [u32p] * 4),
+        "sb200_sign_vargen_bytes": (ci, [vp, i64, u32] + [u32p] * 5),
         "sb200_dbg_fq": (ci, [vp, i64, ci] + [u32p] * 3),
         "sb200_dbg_fr_mul": (ci, [vp, i64] + [u32p] * 3),
         "sb200_dbg_hades": (ci, [vp, i64, ci, u32p]),
@@ -80,7 +84,8 @@ EXPORTED_SYMBOLS = [
     "sb200_launch_count", "sb200_host_alloc", "sb200_host_free", "sb200_verify", "sb200_verify_double",
     "sb200_verify_vargen", "sb200_sign", "sb200_sign_double", "sb200_sign_vargen", "sb200_keygen",
     "sb200_keygen_double", "sb200_keygen_vargen", "sb200_points_decompress", "sb200_points_compress",
-    "sb200_scalars_from_wide", "sb200_fq_to_mont", "sb200_fq_from_mont", "sb200_verify_bytes", "sb200_sign_bytes", "sb200_dbg_fq", "sb200_dbg_fr_mul", "sb200_dbg_hades",
+    "sb200_scalars_from_wide", "sb200_fq_to_mont", "sb200_fq_from_mont", "sb200_verify_bytes", "sb200_sign_bytes",
+    "sb200_verify_double_bytes", "sb200_verify_vargen_bytes", "sb200_sign_double_bytes", "sb200_sign_vargen_bytes", "sb200_dbg_fq", "sb200_dbg_fr_mul", "sb200_dbg_hades",
     "sb200_dbg_scalar_mul",
 ]
 
@@ -297,6 +302,38 @@ class Engine:
         out = aligned_empty((n, 64), dtype=np.uint8)
         self.call("sign_bytes", n, 0, sk.ctypes.data, msg.ctypes.data, nonce.ctypes.data, out.ctypes.data)
         return out
+
+    def _verify_bytes_generic(self, name, pk, pkw, sig, sigw, msg):
+        pk, sig, msg = self._bytes_arr(pk, pkw, "pk"), self._bytes_arr(sig, sigw, "sig"), self._bytes_arr(msg, 32, "msg")
+        n = pk.shape[0]
+        bm = aligned_empty(((n + 31) // 32,)); bm[...] = 0
+        inv = aligned_empty(((n + 31) // 32,)); inv[...] = 0
+        self.call(name, n, 0, pk.ctypes.data, sig.ctypes.data, msg.ctypes.data, bm.ctypes.data, inv.ctypes.data)
+        return self._unpack_bits(bm, n), self._unpack_bits(inv, n)
+
+    def verify_double_bytes(self, pk, sig, msg):
+        """pk n x 64 (pk || pk'), sig n x 96 (u || R || R'), msg n x 32 -> (verdict[n], invalid[n])"""
+        return self._verify_bytes_generic("verify_double_bytes", pk, 64, sig, 96, msg)
+
+    def verify_vargen_bytes(self, pk, sig, msg):
+        """pk n x 64 (pk || generator), sig n x 64 (u || R), msg n x 32 -> (verdict[n], invalid[n])"""
+        return self._verify_bytes_generic("verify_vargen_bytes", pk, 64, sig, 64, msg)
+
+    def sign_double_bytes(self, sk, msg, nonce):
+        sk, msg, nonce = self._bytes_arr(sk, 32, "sk"), self._bytes_arr(msg, 32, "msg"), self._bytes_arr(nonce, 32, "nonce")
+        n = sk.shape[0]
+        out = aligned_empty((n, 96), dtype=np.uint8)
+        self.call("sign_double_bytes", n, 0, sk.ctypes.data, msg.ctypes.data, nonce.ctypes.data, out.ctypes.data)
+        return out
+
+    def sign_vargen_bytes(self, sk, msg, nonce):
+        """sk n x 64 (sk || generator) -> (sig n x 64, generator_ok[n])"""
+        sk, msg, nonce = self._bytes_arr(sk, 64, "sk"), self._bytes_arr(msg, 32, "msg"), self._bytes_arr(nonce, 32, "nonce")
+        n = sk.shape[0]
+        out = aligned_empty((n, 64), dtype=np.uint8)
+        bm = aligned_empty(((n + 31) // 32,)); bm[...] = 0
+        self.call("sign_vargen_bytes", n, 0, sk.ctypes.data, msg.ctypes.data, nonce.ctypes.data, out.ctypes.data, bm.ctypes.data)
+        return out, self._unpack_bits(bm, n)
 
     # ---- building-block probes --------------------------------------------------------------------
     def dbg_fq(self, op: int, a, b=None):

@@ -36,7 +36,8 @@ constexpr int64_t CHUNK = 1 << 18;  // tuples per pipeline stage
 enum Op : int {
   OP_VERIFY = 0, OP_VERIFY_DOUBLE, OP_VERIFY_VARGEN, OP_SIGN, OP_SIGN_DOUBLE, OP_SIGN_VARGEN,
   OP_KEYGEN, OP_KEYGEN_DOUBLE, OP_KEYGEN_VARGEN, OP_DBG_FQ, OP_DBG_FR_MUL, OP_DBG_HADES, OP_DBG_SMUL,
-  OP_DECOMPRESS, OP_COMPRESS, OP_FROM_WIDE, OP_VERIFY_BYTES, OP_SIGN_BYTES, OP_CHALLENGE, OP_VERIFY_EC
+  OP_DECOMPRESS, OP_COMPRESS, OP_FROM_WIDE, OP_VERIFY_BYTES, OP_SIGN_BYTES, OP_CHALLENGE, OP_VERIFY_EC,
+  OP_VERIFY_DOUBLE_BYTES, OP_VERIFY_VARGEN_BYTES, OP_SIGN_DOUBLE_BYTES, OP_SIGN_VARGEN_BYTES
 };
 
 struct KArgs {
@@ -277,6 +278,51 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
     if ((threadIdx.x & 31) == 0 && active) {
       a.bitmap[i >> 5] = word;
       if (a.out[0]) a.out[0][i >> 5] = inv;
+    }
+    return;
+  }
+  if (OP == OP_VERIFY_DOUBLE_BYTES || OP == OP_VERIFY_VARGEN_BYTES) {  // in: pk64, sig96|sig64, msg32 -> bitmap, out0: invalid
+    constexpr int SW = OP == OP_VERIFY_DOUBLE_BYTES ? 24 : 16;
+    uint32_t pk[16], sig[SW], m[8];
+#pragma unroll
+    for (int k = 0; k < 2; k++) ldg_scalar(a.in[0] + i * 16 + 8 * k, pk + 8 * k);
+#pragma unroll
+    for (int k = 0; k < SW / 8; k++) ldg_scalar(a.in[1] + i * SW + 8 * k, sig + 8 * k);
+    ldg_scalar(a.in[2] + i * 8, m);
+    bool invalid, ok;
+    if (OP == OP_VERIFY_DOUBLE_BYTES) ok = verify_double_bytes_core(pk, sig, m, a.combG, a.combGp, invalid);
+    else ok = verify_vargen_bytes_core(pk, sig, m, invalid);
+    unsigned word = __ballot_sync(0xffffffffu, ok && active), inv = __ballot_sync(0xffffffffu, invalid && active);
+    if ((threadIdx.x & 31) == 0 && active) {
+      a.bitmap[i >> 5] = word;
+      if (a.out[0]) a.out[0][i >> 5] = inv;
+    }
+    return;
+  }
+  if (OP == OP_SIGN_DOUBLE_BYTES) {  // in: sk32, msg32, nonce32 -> out0: sig96 = u || R || R'
+    uint32_t sk[8], nonce[8], mb[8], sig[24];
+    ldg_scalar(a.in[0] + i * 8, sk);
+    ldg_scalar(a.in[1] + i * 8, mb);
+    ldg_scalar(a.in[2] + i * 8, nonce);
+    sign_double_bytes_core(sk, mb, nonce, a.combG, a.combGp, sig);
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) stg8(a.out[0] + i * 24 + 8 * k, sig + 8 * k);
+    }
+    return;
+  }
+  if (OP == OP_SIGN_VARGEN_BYTES) {  // in: sk64 (sk || generator), msg32, nonce32 -> out0: sig64, bitmap: generator decoded
+    uint32_t sk[16], nonce[8], mb[8], sig[16];
+    ldg_scalar(a.in[0] + i * 16, sk);
+    ldg_scalar(a.in[0] + i * 16 + 8, sk + 8);
+    ldg_scalar(a.in[1] + i * 8, mb);
+    ldg_scalar(a.in[2] + i * 8, nonce);
+    bool ok = sign_vargen_bytes_core(sk, mb, nonce, sig);
+    unsigned word = __ballot_sync(0xffffffffu, ok && active);
+    if ((threadIdx.x & 31) == 0 && active && a.bitmap) a.bitmap[i >> 5] = word;
+    if (active) {
+      stg8(a.out[0] + i * 16, sig);
+      stg8(a.out[0] + i * 16 + 8, sig + 8);
     }
     return;
   }
@@ -562,6 +608,7 @@ int launch(sb200_ctx* ctx, Op op, const KArgs& a, cudaStream_t st) {
     CASE(OP_VERIFY) CASE(OP_VERIFY_DOUBLE) CASE(OP_VERIFY_VARGEN) CASE(OP_SIGN_VARGEN)
     CASE(OP_KEYGEN_VARGEN) CASE(OP_DBG_FQ) CASE(OP_DBG_FR_MUL) CASE(OP_DBG_HADES)
     CASE(OP_DBG_SMUL) CASE(OP_DECOMPRESS) CASE(OP_COMPRESS) CASE(OP_FROM_WIDE) CASE(OP_VERIFY_BYTES)
+    CASE(OP_VERIFY_DOUBLE_BYTES) CASE(OP_VERIFY_VARGEN_BYTES) CASE(OP_SIGN_DOUBLE_BYTES) CASE(OP_SIGN_VARGEN_BYTES)
 #undef CASE
   }
   ctx->launches.fetch_add(1, std::memory_order_relaxed);
@@ -844,6 +891,36 @@ int sb200_sign_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* s
   if (!sig_out || (flags & SB200_POINTS_AFFINE)) return SB200_ERR_ARG;
   Desc d; d.op = OP_SIGN_BYTES; d.flags = flags; d.nin = 3; d.nout = 1;
   IN(0, (const uint32_t*)sk, 8); IN(1, (const uint32_t*)msg, 8); IN(2, (const uint32_t*)nonce, 8); OUT(0, (uint32_t*)sig_out, 16);
+  return run(ctx, n, d);
+}
+int sb200_verify_double_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg,
+                              uint32_t* verdicts, uint32_t* invalid) {
+  if (!verdicts || (flags & SB200_POINTS_AFFINE)) return SB200_ERR_ARG;
+  Desc d; d.op = OP_VERIFY_DOUBLE_BYTES; d.flags = flags | SB200_POINTS_AFFINE; d.nin = 3; d.nout = 1; d.bitmap = verdicts;
+  IN(0, (const uint32_t*)pk, 16); IN(1, (const uint32_t*)sig, 24); IN(2, (const uint32_t*)msg, 8);
+  d.out[0] = invalid; d.out_words[0] = -1;
+  return run(ctx, n, d);
+}
+int sb200_verify_vargen_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg,
+                              uint32_t* verdicts, uint32_t* invalid) {
+  if (!verdicts || (flags & SB200_POINTS_AFFINE)) return SB200_ERR_ARG;
+  Desc d; d.op = OP_VERIFY_VARGEN_BYTES; d.flags = flags | SB200_POINTS_AFFINE; d.nin = 3; d.nout = 1; d.bitmap = verdicts;
+  IN(0, (const uint32_t*)pk, 16); IN(1, (const uint32_t*)sig, 16); IN(2, (const uint32_t*)msg, 8);
+  d.out[0] = invalid; d.out_words[0] = -1;
+  return run(ctx, n, d);
+}
+int sb200_sign_double_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* sk, const uint8_t* msg, const uint8_t* nonce,
+                            uint8_t* sig_out) {
+  if (!sig_out || (flags & SB200_POINTS_AFFINE)) return SB200_ERR_ARG;
+  Desc d; d.op = OP_SIGN_DOUBLE_BYTES; d.flags = flags; d.nin = 3; d.nout = 1;
+  IN(0, (const uint32_t*)sk, 8); IN(1, (const uint32_t*)msg, 8); IN(2, (const uint32_t*)nonce, 8); OUT(0, (uint32_t*)sig_out, 24);
+  return run(ctx, n, d);
+}
+int sb200_sign_vargen_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* sk, const uint8_t* msg, const uint8_t* nonce,
+                            uint8_t* sig_out, uint32_t* ok_bitmap) {
+  if (!sig_out || !ok_bitmap || (flags & SB200_POINTS_AFFINE)) return SB200_ERR_ARG;
+  Desc d; d.op = OP_SIGN_VARGEN_BYTES; d.flags = flags | SB200_POINTS_AFFINE; d.nin = 3; d.nout = 1; d.bitmap = ok_bitmap;
+  IN(0, (const uint32_t*)sk, 16); IN(1, (const uint32_t*)msg, 8); IN(2, (const uint32_t*)nonce, 8); OUT(0, (uint32_t*)sig_out, 16);
   return run(ctx, n, d);
 }
 int sb200_dbg_fq(sb200_ctx* ctx, int64_t n, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {

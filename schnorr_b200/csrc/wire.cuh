@@ -208,4 +208,82 @@ SB_HD bool verify_bytes_core(const uint32_t* pk32, const uint32_t* sig64, const 
   return ok & verdict;
 }
 
+// canonical message bytes -> Montgomery field element; false <=> BlsScalar::from_bytes fails (>= q)
+SB_HD bool msg_from_bytes(const uint32_t* msg32, fq& m) {
+  uint32_t mb[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) mb[i] = msg32[i];
+  bool ok = lt_q(mb);
+  fq mc;
+#pragma unroll
+  for (int i = 0; i < 8; i++) mc.v[i] = ok ? mb[i] : 0u;
+  m = fq_to_mont(mc);
+  return ok;
+}
+SB_HD bool point_from_bytes(const uint32_t* b32, point_in& P) {
+  P.affine = true;
+  P.Z = fq_one();
+  return point_decompress(b32, P.U, P.V);
+}
+
+// PublicKeyDouble::from_bytes (pk || pk', /root/reference/src/keys/public.rs:282-299) +
+// SignatureDouble::from_bytes (u || R || R', /root/reference/src/signatures.rs:245-270) + verify (public.rs:222-244)
+SB_HD bool verify_double_bytes_core(const uint32_t* pk64, const uint32_t* sig96, const uint32_t* msg32, const uint32_t* combG,
+                                    const uint32_t* combGp, bool& invalid) {
+  point_in PK, PKp, R, Rp;
+  bool ok = point_from_bytes(pk64, PK);
+  ok &= point_from_bytes(pk64 + 8, PKp);
+  ok &= point_from_bytes(sig96 + 8, R);
+  ok &= point_from_bytes(sig96 + 16, Rp);
+  uint32_t u[8], c[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) u[i] = sig96[i];
+  fq m;
+  ok &= scalar_lt_r(u) & msg_from_bytes(msg32, m);
+  invalid = !ok;
+  bool verdict = verify_double_core(PK, PKp, u, R, Rp, m, combG, combGp, c);
+  return ok & verdict;
+}
+
+// PublicKeyVarGen::from_bytes (pk || generator, public.rs:347-372) + SignatureVarGen::from_bytes (u || R,
+// signatures.rs:387-404) + verify (public.rs:401-415)
+SB_HD bool verify_vargen_bytes_core(const uint32_t* pk64, const uint32_t* sig64, const uint32_t* msg32, bool& invalid) {
+  point_in PK, GEN, R;
+  bool ok = point_from_bytes(pk64, PK);
+  ok &= point_from_bytes(pk64 + 8, GEN);
+  ok &= point_from_bytes(sig64 + 8, R);
+  uint32_t u[8], c[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) u[i] = sig64[i];
+  fq m;
+  ok &= scalar_lt_r(u) & msg_from_bytes(msg32, m);
+  invalid = !ok;
+  bool verdict = verify_vargen_core(PK, GEN, u, R, m, c);
+  return ok & verdict;
+}
+
+// SecretKey::sign_double -> SignatureDouble::to_bytes (secret.rs:217-240, signatures.rs:245-258): sig96 = u || R || R'
+SB_HD void sign_double_bytes_core(const uint32_t* sk32, const uint32_t* msg32, const uint32_t* nonce32, const uint32_t* combG,
+                                  const uint32_t* combGp, uint32_t* sig96) {
+  fq m, Ru, Rv, Rpu, Rpv;
+  uint32_t c[8];
+  msg_from_bytes(msg32, m);
+  sign_double_core(sk32, nonce32, m, combG, combGp, sig96, Ru, Rv, Rpu, Rpv, c);
+  point_compress(Ru, Rv, sig96 + 8);
+  point_compress(Rpu, Rpv, sig96 + 16);
+}
+
+// SecretKeyVarGen::from_bytes (sk || generator, secret.rs:313-336) + sign (secret.rs:433-451) +
+// SignatureVarGen::to_bytes: sig64 = u || R.  false <=> the generator does not decode.
+SB_HD bool sign_vargen_bytes_core(const uint32_t* sk64, const uint32_t* msg32, const uint32_t* nonce32, uint32_t* sig64) {
+  point_in GEN;
+  bool ok = point_from_bytes(sk64 + 8, GEN);
+  fq m, Ru, Rv;
+  uint32_t c[8];
+  msg_from_bytes(msg32, m);
+  sign_vargen_core(sk64, GEN, nonce32, m, sig64, Ru, Rv, c);
+  point_compress(Ru, Rv, sig64 + 8);
+  return ok;
+}
+
 }  // namespace sb200

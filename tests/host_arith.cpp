@@ -100,6 +100,16 @@ int h_fq_sqrt(const uint32_t* a, uint32_t* r) { fq x; bool ok = fq_sqrt(L(a), x)
 int h_verify_bytes(const uint32_t* pk, const uint32_t* sig, const uint32_t* msg, const uint32_t* combG, int* invalid) {
   bool inv; bool ok = verify_bytes_core(pk, sig, msg, combG, inv); *invalid = inv; return ok;
 }
+int h_verify_double_bytes(const uint32_t* pk, const uint32_t* sig, const uint32_t* msg, const uint32_t* combG, const uint32_t* combGp, int* invalid) {
+  bool inv; bool ok = verify_double_bytes_core(pk, sig, msg, combG, combGp, inv); *invalid = inv; return ok;
+}
+int h_verify_vargen_bytes(const uint32_t* pk, const uint32_t* sig, const uint32_t* msg, int* invalid) {
+  bool inv; bool ok = verify_vargen_bytes_core(pk, sig, msg, inv); *invalid = inv; return ok;
+}
+void h_sign_double_bytes(const uint32_t* sk, const uint32_t* msg, const uint32_t* nonce, const uint32_t* combG, const uint32_t* combGp, uint32_t* sig96) {
+  sign_double_bytes_core(sk, msg, nonce, combG, combGp, sig96);
+}
+int h_sign_vargen_bytes(const uint32_t* sk64, const uint32_t* msg, const uint32_t* nonce, uint32_t* sig64) { return sign_vargen_bytes_core(sk64, msg, nonce, sig64); }
 void h_fixed_mul(const uint32_t* comb, const uint32_t* k, uint32_t* uv) {
   fq a, b; ext_to_affine(fixed_base_mul(comb, k), a, b); S(uv, a); S(uv + 8, b);
 }

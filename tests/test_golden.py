@@ -89,6 +89,30 @@ def test_c_restatement_matches_golden():
     assert ok.tolist() == [e["valid"] for e in es]
 
 
+def test_host_build_wire_level_double_and_vargen():
+    """the byte-level cores of the double-key and variable-generator schemes (CPU build of the kernels' code)"""
+    import ctypes
+    import hostlib as H
+    lib = H.build()
+    tabs = H.comb_tables(lib)
+    W = lambda h: H.ptr(np.frombuffer(bytes.fromhex(h), np.uint32).copy())
+    inv = ctypes.c_int(0)
+    for g in GOLD["double"][:3]:
+        sig = np.zeros(24, np.uint32)
+        lib.h_sign_double_bytes(W(g["sk"]), W(g["msg"]), W(g["nonce"]), H.ptr(tabs[0]), H.ptr(tabs[1]), H.ptr(sig))
+        assert sig.tobytes().hex() == g["sig"]
+        assert lib.h_verify_double_bytes(W(g["pk"]), W(g["sig"]), W(g["msg"]), H.ptr(tabs[0]), H.ptr(tabs[1]), ctypes.byref(inv)) == 1 and inv.value == 0
+        swapped = g["pk"][64:] + g["pk"][:64]
+        assert lib.h_verify_double_bytes(W(swapped), W(g["sig"]), W(g["msg"]), H.ptr(tabs[0]), H.ptr(tabs[1]), ctypes.byref(inv)) == 0 and inv.value == 0
+    for g in GOLD["vargen"][:3]:
+        sig = np.zeros(16, np.uint32)
+        assert lib.h_sign_vargen_bytes(W(g["sk"]), W(g["msg"]), W(g["nonce"]), H.ptr(sig)) == 1
+        assert sig.tobytes().hex() == g["sig"]
+        assert lib.h_verify_vargen_bytes(W(g["pk"]), W(g["sig"]), W(g["msg"]), ctypes.byref(inv)) == 1 and inv.value == 0
+        bad = g["sig"][:64] + (2).to_bytes(32, "little").hex()  # v = 2 is not on the curve
+        assert lib.h_verify_vargen_bytes(W(g["pk"]), W(bad), W(g["msg"]), ctypes.byref(inv)) == 0 and inv.value == 1
+
+
 # ------------------------------------------------------------------ GPU: the CUDA path against the file
 def _b(hexes, width):
     return np.frombuffer(b"".join(bytes.fromhex(h) for h in hexes), dtype=np.uint8).reshape(-1, width)
@@ -131,3 +155,33 @@ def test_gpu_double_and_vargen(engine):
     assert [bytes(a).hex() + g["sk"][64:] for a, g in zip(engine.points_compress(pk), gs)] == [g["pk"] for g in gs]
     ok, _ = engine.verify_vargen(pk, gen, u, Rr, msg)
     assert ok.all()
+
+
+@pytest.mark.gpu
+def test_gpu_double_and_vargen_wire_level(engine):
+    """SignatureDouble / PublicKeyDouble / SignatureVarGen / PublicKeyVarGen / SecretKeyVarGen in their to_bytes() forms"""
+    gs = GOLD["double"]
+    sig = engine.sign_double_bytes(_b([g["sk"] for g in gs], 32), _b([g["msg"] for g in gs], 32), _b([g["nonce"] for g in gs], 32))
+    assert [bytes(r).hex() for r in sig] == [g["sig"] for g in gs]
+    pks = [g["pk"] for g in gs]
+    sigs = [g["sig"] for g in gs]
+    msgs = [g["msg"] for g in gs]
+    # tuple 1: keys swapped (false); tuple 2: R' not on the curve (invalid); tuple 3: u >= r (invalid); tuple 4: msg >= q (invalid)
+    pks[1] = pks[1][64:] + pks[1][:64]
+    sigs[2] = sigs[2][:128] + (2).to_bytes(32, "little").hex()
+    sigs[3] = R.to_bytes(32, "little").hex() + sigs[3][64:]
+    msgs[4] = Q.to_bytes(32, "little").hex()
+    ok, invalid = engine.verify_double_bytes(_b(pks, 64), _b(sigs, 96), _b(msgs, 32))
+    assert ok.tolist() == [True, False, False, False, False, True, True, True]
+    assert invalid.tolist() == [False, False, True, True, True, False, False, False]
+
+    gs = GOLD["vargen"]
+    sig, gen_ok = engine.sign_vargen_bytes(_b([g["sk"] for g in gs], 64), _b([g["msg"] for g in gs], 32), _b([g["nonce"] for g in gs], 32))
+    assert gen_ok.all() and [bytes(r).hex() for r in sig] == [g["sig"] for g in gs]
+    pks = [g["pk"] for g in gs]
+    sigs = [g["sig"] for g in gs]
+    pks[1] = gs[2]["pk"][:64] + pks[1][64:]                       # another key, same generator slot: false
+    pks[2] = pks[2][:64] + (2).to_bytes(32, "little").hex()      # generator does not decode: invalid
+    ok, invalid = engine.verify_vargen_bytes(_b(pks, 64), _b(sigs, 64), _b([g["msg"] for g in gs], 32))
+    assert ok.tolist() == [True, False, False, True, True, True, True, True]
+    assert invalid.tolist() == [False, False, True, False, False, False, False, False]
