@@ -71,12 +71,7 @@ SB_HD proj p1p1_to_proj(const p1p1& c) {
     r.X = fq_mul_inl(c.E, c.F);
     r.Y = fq_mul_inl(c.G, c.H);
   } else {
-#if SB_MUL_CLONES
-    r.X = fq_mul(c.E, c.F);
-    r.Y = fq_mul_b(c.G, c.H);
-#else
     fq_mul2(c.E, c.F, c.G, c.H, r.X, r.Y);
-#endif
   }
   r.Z = mulT<INL>(c.F, c.G);
   return r;
@@ -106,15 +101,8 @@ SB_HD p1p1 ed_dbl(const fq& X, const fq& Y, const fq& Z) {
     C = fq_sqr_inl(Z);
     S = fq_sqr_inl(fq_add(X, Y));
   } else {
-#if SB_MUL_CLONES
-    A = fq_sqr(X);
-    B = fq_sqr_b(Y);
-    C = fq_sqr(Z);
-    S = fq_sqr_b(fq_add(X, Y));
-#else
     fq_sqr2(X, Y, A, B);
     fq_sqr2(Z, fq_add(X, Y), C, S);
-#endif
   }
   C = fq_dbl(C);
   p1p1 r;

@@ -808,9 +808,6 @@ SB_HD fq fq_dot5_inl(const uint32_t (*cst)[8], const fq& s0, const fq& s1, const
 #ifndef SB_MUL_NOINLINE
 #define SB_MUL_NOINLINE 1
 #endif
-#ifndef SB_MUL_CLONES
-#define SB_MUL_CLONES 0  // measured: 29 fewer moves per doubling, but +7.4 KB of hot code: 19.05 -> 17.8 M verifies/s
-#endif
 #if defined(__CUDACC__) && SB_MUL_NOINLINE
 #ifndef SB_MUL_BYPTR
 #define SB_MUL_BYPTR 0  // experiment: operands through local memory instead of the register ABI
@@ -823,33 +820,10 @@ static __device__ __forceinline__ fq fq_sqr_ool(const fq& a) { fq r; fq_sqr_ptr(
 #else
 static __device__ __noinline__ fq fq_mul_ool(fq a, fq b) { return fq_mul_inl(a, b); }
 static __device__ __noinline__ fq fq_sqr_ool(fq a) { return fq_sqr_inl(a); }
-#if SB_MUL_CLONES
-// experiment: second copies of the two bodies, so that ptxas may give them other parameter registers and a caller can
-// keep one call's result in place while the next call runs
-static __device__ __noinline__ fq fq_mul_ool_b(fq b, fq a) { return fq_mul_inl(a, b); }
-static __device__ __noinline__ fq fq_sqr_ool_b(fq pad, fq a) { (void)pad; return fq_sqr_inl(a); }
-#endif
 #endif
 static __device__ __noinline__ fq fq_dot5_ool(const uint32_t (*cst)[8], fq s0, fq s1, fq s2, fq s3, fq s4) {
   return fq_dot5_inl(cst, s0, s1, s2, s3, s4);
 }
-// The same dot product as two small bodies called 5 + 1 times (4.5 KB instead of one 13.6 KB body): the curve loop,
-// both multipliers and the hash loop then fit the 32 KB L1.5 instruction cache together.
-#ifndef SB_DOT5_SPLIT
-#define SB_DOT5_SPLIT 0  // measured: verify +0.5 %, sign_bytes -5 %: within noise once the doubling loop is rolled
-#endif
-struct fq_acc17 {
-  uint32_t v[17];
-};
-static __device__ __noinline__ fq_acc17 fq_mulacc_ool(fq_acc17 S, fq s, const uint32_t* cst) {
-  uint32_t T[16], c[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) c[i] = cst[i];
-  mul_wide16(T, s.v, c);
-  acc17(S.v, T);
-  return S;
-}
-static __device__ __noinline__ fq fq_reduce17_ool(fq_acc17 S) { return mont_reduce17(S.v); }
 #endif
 SB_HD fq fq_mul(const fq& a, const fq& b) {
 #if defined(__CUDA_ARCH__) && SB_MUL_NOINLINE
@@ -859,17 +833,7 @@ SB_HD fq fq_mul(const fq& a, const fq& b) {
 #endif
 }
 SB_HD fq fq_dot5(const uint32_t (*cst)[8], const fq& s0, const fq& s1, const fq& s2, const fq& s3, const fq& s4) {
-#if defined(__CUDA_ARCH__) && SB_MUL_NOINLINE && SB_DOT5_SPLIT
-  fq_acc17 S;
-#pragma unroll
-  for (int i = 0; i < 17; i++) S.v[i] = 0;
-  S = fq_mulacc_ool(S, s0, cst[0]);
-  S = fq_mulacc_ool(S, s1, cst[1]);
-  S = fq_mulacc_ool(S, s2, cst[2]);
-  S = fq_mulacc_ool(S, s3, cst[3]);
-  S = fq_mulacc_ool(S, s4, cst[4]);
-  return fq_reduce17_ool(S);
-#elif defined(__CUDA_ARCH__) && SB_MUL_NOINLINE
+#if defined(__CUDA_ARCH__) && SB_MUL_NOINLINE
   return fq_dot5_ool(cst, s0, s1, s2, s3, s4);
 #else
   return fq_dot5_inl(cst, s0, s1, s2, s3, s4);
@@ -924,23 +888,6 @@ SB_HD void fq_sqr2(const fq& a, const fq& b, fq& r0, fq& r1) {
 #else
   r0 = fq_sqr(a);
   r1 = fq_sqr(b);
-#endif
-}
-
-// clone selectors (SB_MUL_CLONES experiment): the "b" flavours call the second copies of the bodies
-SB_HD fq fq_mul_b(const fq& a, const fq& b) {
-#if defined(__CUDA_ARCH__) && SB_MUL_NOINLINE && SB_MUL_CLONES
-  return fq_mul_ool_b(b, a);
-#else
-  return fq_mul(a, b);
-#endif
-}
-SB_HD fq fq_sqr_b(const fq& a) {
-#if defined(__CUDA_ARCH__) && SB_MUL_NOINLINE && SB_MUL_CLONES
-  fq pad = a;
-  return fq_sqr_ool_b(pad, a);
-#else
-  return fq_sqr(a);
 #endif
 }
 

@@ -92,40 +92,11 @@ SB_HD void hades_perm_dense(fq* s) {
   for (int r = 0; r < 4; r++, rc += 5) hades_full_round<false>(s, rc);
 }
 
-// One copy of the full round for both ends of the permutation (two inlined copies are 2 x 10 KB of a 32 KB
-// instruction cache that also has to hold the curve loop and the multipliers).
-#ifndef SB_FULL_ROUND_OOL
-#define SB_FULL_ROUND_OOL 0  // measured neutral (19.04 vs 18.96 M verifies/s)
-#endif
-struct hades_state {
-  fq w[5];
-};
-#if defined(__CUDACC__)
-static __device__ __noinline__ hades_state hades_full_rounds4_ool(hades_state st, int rc) {
-#pragma unroll 1
-  for (int r = 0; r < 4; r++, rc += 5) hades_full_round(st.w, rc);
-  return st;
-}
-#endif
-SB_HD void hades_full_rounds4(fq* s, int rc) {
-#if defined(__CUDA_ARCH__) && SB_FULL_ROUND_OOL
-  hades_state st;
-#pragma unroll
-  for (int k = 0; k < 5; k++) st.w[k] = s[k];
-  st = hades_full_rounds4_ool(st, rc);
-#pragma unroll
-  for (int k = 0; k < 5; k++) s[k] = st.w[k];
-#else
-#pragma unroll 1
-  for (int r = 0; r < 4; r++, rc += 5) hades_full_round(s, rc);
-#endif
-}
-
 // Production permutation: sparse partial rounds.
 SB_HD void hades_perm(fq* s) {
   int rc = 0;
-  hades_full_rounds4(s, rc);
-  rc += 20;
+#pragma unroll 1
+  for (int r = 0; r < 4; r++, rc += 5) hades_full_round(s, rc);
 #pragma unroll
   for (int k = 0; k < 4; k++) s[k] = fq_add(s[k], ld8(SB_CONST(hades_pre)[k]));
 #pragma unroll 1
@@ -139,7 +110,8 @@ SB_HD void hades_perm(fq* s) {
   }
   SB_MATMUL5(s, hades_post);
   rc += 59 * 5;
-  hades_full_rounds4(s, rc);
+#pragma unroll 1
+  for (int r = 0; r < 4; r++, rc += 5) hades_full_round(s, rc);
 }
 
 // low 250 bits of the canonical integer (dusk_poseidon::sponge::truncated), as a scalar
