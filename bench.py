@@ -251,7 +251,8 @@ def main():
         roof = {"bound": "imad", "achieved": achieved, "peak": peak["imad_wide_per_s"] / 1e12, "unit": "T IMAD.WIDE/s",
                 "frac": achieved / (peak["imad_wide_per_s"] / 1e12), "traffic": ncu_traffic(n),
                 "peak_source": "IMAD_PEAK.json (tools/imad_peak.cu measured on this pool's B200: IMAD.WIDE carry-chain issue rate)",
-                "work": f"{wide} IMAD.WIDE.U32 per verification ({ops['fq_mul']} fq_mul, {ops['fq_sqr']} fq_sqr, {ops.get('fq_dot5', 0)} fq_dot5)",
+                "work": f"{wide} IMAD.WIDE.U32 per verification ({ops['fq_mul']} fq_mul, {ops['fq_sqr']} fq_sqr, {ops.get('fq_dot5', 0)} fq_dot5, "
+                        f"{ops.get('fr_mont_mul', 0)} fr_mont_mul, the rest the half-size-scalar Euclid)",
                 "hbm": {"achieved_gbs": (h2d + d2h) / (ms_step * 1e-3) / 1e9,
                         "peak_gbs": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
                         if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0}}

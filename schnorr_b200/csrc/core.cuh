@@ -12,6 +12,7 @@
 #include "ed.cuh"
 #include "hades.cuh"
 #include "hades_fd.cuh"
+#include "hgcd.cuh"
 
 namespace sb200 {
 
@@ -88,6 +89,66 @@ SB_HD bool verify_ec_core(const point_in& PK, const uint32_t* u_in, const point_
   return ok & p1p1_equals(cp, R);
 }
 
+// The same predicate with half-size scalars (hgcd.cuh):  (b u mod r) G + a PK - b R == identity  for  a = b c (mod 8r),
+// b odd: two variable-base tables, 34 windows (132 doublings) instead of 63 (248).  `fast_ok` = false where the
+// short vector does not fit the window budget; the caller then uses verify_ec_core for that tuple.
+SB_HD point_in point_neg(const point_in& p) {
+  point_in r = p;
+  r.U = fq_neg(p.U);
+  return r;
+}
+SB_HD bool verify_ec_core_fast(const point_in& PK, const uint32_t* u_in, const point_in& R, const uint32_t* c_in,
+                               const uint32_t* combG, bool& fast_ok) {
+  bool ok = scalar_lt_r(u_in);
+  hgcd_res h = half_gcd_8r(c_in);
+  fast_ok = h.ok;
+  fr bb, uu;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    bb.v[i] = h.b[i];
+    uu.v[i] = ok ? u_in[i] : 0u;
+  }
+  fr w = fr_mul(bb, uu);  // |b| u mod r
+  if (h.bneg) {           // b u = -(|b| u)
+    fr z;
+#pragma unroll
+    for (int i = 0; i < 8; i++) z.v[i] = 0;
+    w = fr_sub(z, w);
+  }
+  pniels tabs[2][9];  // [0]: multiples of -sign(b) R (|b| of them make -b R), [1]: multiples of PK
+  pniels *tabR = tabs[0], *tabP = tabs[1];
+  {
+    const point_in nR = h.bneg ? R : point_neg(R);
+#pragma unroll 1
+    for (int t = 0; t < 2; t++) vartable_build(tabs[t], point_to_ext(t ? PK : nR));  // one copy of the table code
+  }
+  recode_offset<4>(h.a);
+  recode_offset<4>(h.b);
+  p1p1 cp = ed_mul_var2_rolled(tabR, h.b, tabP, h.a, 34);
+  recode_offset<COMB_BITS>(w.v);
+  cp = ed_comb_add(p1p1_to_ext(cp), combG, w.v);
+  // identity <=> X = E F = 0 and Y = G H = Z = F G with F, G != 0 (complete addition) <=> E = 0 and H = F
+  return ok & fq_is_zero(cp.E) & fq_eq(cp.H, cp.F);
+}
+
+#ifndef SB_VERIFY_HGCD
+#define SB_VERIFY_HGCD 1
+#endif
+// c PK + u G == R, by the half-size form where it applies
+SB_HD bool verify_ec(const point_in& PK, const uint32_t* u_in, const point_in& R, const uint32_t* c_in, const uint32_t* combG) {
+#if SB_VERIFY_HGCD
+  bool fast_ok;
+  bool ok = verify_ec_core_fast(PK, u_in, R, c_in, combG, fast_ok);
+  if (SB_WARP_ANY(!fast_ok)) {
+    bool slow = verify_ec_core(PK, u_in, R, c_in, combG);
+    ok = fast_ok ? ok : slow;
+  }
+  return ok;
+#else
+  return verify_ec_core(PK, u_in, R, c_in, combG);
+#endif
+}
+
 // the hash half: c = H(R_affine, m)
 SB_HD void verify_hash_core(const point_in& R, const fq& m, uint32_t* c_out) {
   fq ru, rv;
@@ -104,7 +165,7 @@ SB_HD void verify_hash_core_fd(const point_in& R, const fq& m, uint32_t* c_out, 
 SB_HD bool verify_core(const point_in& PK, const uint32_t* u_in, const point_in& R, const fq& m, const uint32_t* combG,
                        uint32_t* c_out) {
   verify_hash_core(R, m, c_out);
-  return verify_ec_core(PK, u_in, R, c_out, combG);
+  return verify_ec(PK, u_in, R, c_out, combG);
 }
 
 SB_HD bool verify_vargen_core(const point_in& PK, const point_in& GEN, const uint32_t* u_in, const point_in& R,

@@ -318,6 +318,26 @@ SB_HD p1p1 ed_mul_var2(const pniels* tab1, const uint32_t* k1_rec, const pniels*
   return c;
 }
 
+// The same with the two additions of a window as a 2-trip loop: one copy of the conversion + lookup + addition
+// sequence in the hot loop (7 KB less code in a 32 KB instruction cache).
+SB_HD p1p1 ed_mul_var2_rolled(const pniels* tab1, const uint32_t* k1_rec, const pniels* tab2, const uint32_t* k2_rec, int nwin) {
+  p1p1 c = ed_add(ext_identity(), vartable_lookup(tab1, recode_digit<4>(k1_rec, nwin - 1)));
+  c = ed_add(p1p1_to_ext(c), vartable_lookup(tab2, recode_digit<4>(k2_rec, nwin - 1)));
+#pragma unroll 1
+  for (int i = nwin - 2; i >= 0; i--) {
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) c = pt_dbl(c);
+#pragma unroll 1
+    for (int t = 0; t < 2; t++) {
+      const pniels* tab = t ? tab2 : tab1;
+      const uint32_t* kr = t ? k2_rec : k1_rec;
+      ext e = p1p1_to_ext(c);
+      c = ed_add(e, vartable_lookup(tab, recode_digit<4>(kr, i)));
+    }
+  }
+  return c;
+}
+
 // ------------------------------------------------------------------------------------------
 // fixed-base comb.  Table layout: window j, entry e (0..2^(W-1)) = e * 2^(W*j) * B in affine Niels form,
 // entry 0 = identity; 96 bytes per entry.  acc += k * B with k offset-recoded (W = COMB_BITS).

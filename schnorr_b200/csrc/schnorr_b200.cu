@@ -29,7 +29,10 @@ constexpr int TPB = 128;
 #endif
 // CTAs per SM the register allocator must allow: 4 (128 registers/thread) everywhere except the two kernels that
 // keep a second point table live, which measure faster at 3 (168 registers, fewer spills).  [A/B timed on B200]
-constexpr int min_ctas(int op) { return (op == 1 || op == 2) ? SB_MIN_CTAS - 1 : SB_MIN_CTAS; }
+#ifndef SB_VERIFY_CTAS
+#define SB_VERIFY_CTAS SB_MIN_CTAS
+#endif
+constexpr int min_ctas(int op) { return (op == 0 || op == 19) ? SB_VERIFY_CTAS : (op == 1 || op == 2) ? SB_MIN_CTAS - 1 : SB_MIN_CTAS; }
 constexpr int MAX_IN = 6, MAX_OUT = 4;
 constexpr int64_t CHUNK = 1 << 18;  // tuples per pipeline stage
 
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
     uint32_t u[8];
     ldg_scalar(a.in[1] + i * 8, u);
     ldg_scalar(a.out[0] + i * 8, c);
-    bool ok = verify_ec_core(ldg_point(a.in[0], i, aff), u, ldg_point(a.in[2], i, aff), c, a.combG);
+    bool ok = verify_ec(ldg_point(a.in[0], i, aff), u, ldg_point(a.in[2], i, aff), c, a.combG);
     unsigned word = __ballot_sync(0xffffffffu, ok && active);
     if ((threadIdx.x & 31) == 0 && active) a.bitmap[i >> 5] = word;
     return;
@@ -364,7 +367,7 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
 #define SB_VERIFY_WS 1
 #endif
 #ifndef SB_VERIFY_SPLIT
-#define SB_VERIFY_SPLIT 0  // measured: 19.02 vs 19.04 M verifies/s -- once the doubling loop is rolled the phases no longer evict each other
+#define SB_VERIFY_SPLIT 1  // hash and curve halves as two launches: with the half-size curve path the single kernel's phases evict each other from the instruction cache (21.1 -> 22.9 M verifies/s)
 #endif
 #ifndef SB_WS_SETMAXNREG
 #define SB_WS_SETMAXNREG 0
@@ -540,6 +543,8 @@ struct DevCtx {
   uint8_t* arena[2] = {nullptr, nullptr};
   size_t arena_cap[2] = {0, 0};
   WsState* ws[3] = {nullptr, nullptr, nullptr};  // per pipeline stream, [2] = caller's stream (SB200_DEVICE_PTRS)
+  uint32_t* cscratch = nullptr;                  // challenges of a SB200_DEVICE_PTRS verify call without c_out
+  size_t cscratch_cap = 0;
   int nsm = 0;
 };
 
@@ -592,7 +597,7 @@ int launch(sb200_ctx* ctx, Op op, const KArgs& a, cudaStream_t st) {
   }
 #endif
 #if SB_VERIFY_SPLIT
-  if (op == OP_VERIFY && a.out[0]) {
+  if (op == OP_VERIFY) {  // a.out[0] is always set here: the caller's c_out or scratch
     k_run<OP_CHALLENGE><<<grid, TPB, 0, st>>>(a);
     k_run<OP_VERIFY_EC><<<grid, TPB, 0, st>>>(a);
     ctx->launches.fetch_add(2, std::memory_order_relaxed);
@@ -635,6 +640,19 @@ int run(sb200_ctx* ctx, int64_t n, const Desc& d) {
     a.ws = dc.ws[2]; a.nsm = dc.nsm;
     for (int k = 0; k < d.nin; k++) a.in[k] = d.in[k];
     for (int k = 0; k < d.nout; k++) a.out[k] = d.out[k];
+#if SB_VERIFY_SPLIT
+    if (d.op == OP_VERIFY && !(d.flags & SB200_VERIFY_DUAL_PIPE) && !a.out[0]) {  // hash and curve kernels hand c over in memory
+      size_t need = (size_t)n * 32;
+      if (dc.cscratch_cap < need) {
+        CU(cudaStreamSynchronize(ctx->user_stream));
+        if (dc.cscratch) CU(cudaFree(dc.cscratch));
+        dc.cscratch = nullptr; dc.cscratch_cap = 0;
+        if (cudaMalloc(&dc.cscratch, need) != cudaSuccess) { ctx->err = "cudaMalloc challenge scratch"; return SB200_ERR_NOMEM; }
+        dc.cscratch_cap = need;
+      }
+      a.out[0] = dc.cscratch;
+    }
+#endif
     return launch(ctx, d.op, a, ctx->user_stream);
   }
 
@@ -642,6 +660,8 @@ int run(sb200_ctx* ctx, int64_t n, const Desc& d) {
   size_t per_tuple = 0;
   for (int k = 0; k < d.nin; k++) per_tuple += (size_t)d.in_words[k] * 4;
   for (int k = 0; k < d.nout; k++) per_tuple += (d.out[k] && d.out_words[k] > 0) ? (size_t)d.out_words[k] * 4 : 0;
+  const bool c_scratch = SB_VERIFY_SPLIT && d.op == OP_VERIFY && !d.out[0];  // device-only challenge rows between the two kernels
+  if (c_scratch) per_tuple += 32;
 
   const int ndev = (int)ctx->devs.size();
   int64_t per_dev = ((n + ndev - 1) / ndev + 31) & ~(int64_t)31;
@@ -681,6 +701,7 @@ int run(sb200_ctx* ctx, int64_t n, const Desc& d) {
       };
       for (int k = 0; k < d.nout; k++)
         if (d.out[k]) a.out[k] = dout[k] = (uint32_t*)carve(out_bytes(k));
+      if (c_scratch) a.out[0] = (uint32_t*)carve((size_t)cn * 32);
       uint32_t* dbm = nullptr;
       if (d.bitmap) a.bitmap = dbm = (uint32_t*)carve((size_t)((cn + 31) / 32) * 4);
       int rc = launch(ctx, d.op, a, st);
@@ -755,6 +776,7 @@ void sb200_destroy(sb200_ctx* ctx) {
     if (dc.combGp) cudaFree(dc.combGp);
     for (int s = 0; s < 3; s++)
       if (dc.ws[s]) cudaFree(dc.ws[s]);
+    if (dc.cscratch) cudaFree(dc.cscratch);
   }
   delete ctx;
 }

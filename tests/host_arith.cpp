@@ -110,6 +110,17 @@ void h_sign_double_bytes(const uint32_t* sk, const uint32_t* msg, const uint32_t
   sign_double_bytes_core(sk, msg, nonce, combG, combGp, sig96);
 }
 int h_sign_vargen_bytes(const uint32_t* sk64, const uint32_t* msg, const uint32_t* nonce, uint32_t* sig64) { return sign_vargen_bytes_core(sk64, msg, nonce, sig64); }
+// half-size scalars: out = a[8] | b[8] | bneg | ok
+void h_half_gcd(const uint32_t* c, uint32_t* out) {
+  hgcd_res r = half_gcd_8r(c);
+  memcpy(out, r.a, 32); memcpy(out + 8, r.b, 32); out[16] = r.bneg; out[17] = r.ok;
+}
+int h_verify_ec(const uint32_t* pk, const uint32_t* u, const uint32_t* R, const uint32_t* c, int affine, const uint32_t* combG, int fast, int* fast_ok) {
+  bool fo = true;
+  bool ok = fast ? verify_ec_core_fast(P(pk, affine), u, P(R, affine), c, combG, fo) : verify_ec_core(P(pk, affine), u, P(R, affine), c, combG);
+  *fast_ok = fo;
+  return ok;
+}
 void h_fixed_mul(const uint32_t* comb, const uint32_t* k, uint32_t* uv) {
   fq a, b; ext_to_affine(fixed_base_mul(comb, k), a, b); S(uv, a); S(uv + 8, b);
 }

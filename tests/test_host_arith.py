@@ -254,3 +254,63 @@ def test_challenge_fd_pair(lib):
         mm = np.concatenate([H.mont(x) for x in m])
         lib.h_challenge3_pair(H.ptr(ru), H.ptr(rv), H.ptr(mm), H.ptr(out))
         assert [H.to_int(out[:8]), H.to_int(out[8:])] == [o.challenge_hash(P[0], m[0]), o.challenge_hash(P[1], m[1])]
+
+
+# ---- half-size scalars for verification (csrc/hgcd.cuh) --------------------------------------------------------
+def test_half_gcd_invariants(lib):
+    """a = b c (mod 8r), 0 <= a < 2^134, |b| < 2^134, b odd -- or ok = 0 (the caller then takes the full-size path)"""
+    rnd = random.Random(21)
+    N = 8 * R
+    out = np.zeros(18, np.uint32)
+    cases = [0, 1, 2, 3, (1 << 128) - 1, 1 << 128, (1 << 128) + 1, (1 << 250) - 1, N // 2 % (1 << 250), N // 3, (N // 3) * 2 % (1 << 250),
+             (1 << 249), 8, 16, R % (1 << 250), (N - 1) % (1 << 250)]
+    cases += [rnd.randrange(1 << 250) for _ in range(400)]
+    cases += [rnd.randrange(1 << 130) for _ in range(50)]               # barely above the bound: few steps
+    cases += [pow(rnd.randrange(1, 1 << 20), -1, N) % (1 << 250) if False else (N // rnd.randrange(2, 1 << 40)) % (1 << 250) for _ in range(100)]  # N / small: huge first quotients
+    n_ok = 0
+    for c in cases:
+        lib.h_half_gcd(H.ptr(H.limbs(c)), H.ptr(out))
+        a, b = H.to_int(out[:8]), H.to_int(out[8:16])
+        bneg, ok = int(out[16]), int(out[17])
+        if not ok:
+            continue
+        n_ok += 1
+        bs = -b if bneg else b
+        assert a < (1 << 134) and b < (1 << 134) and b % 2 == 1, (c, a, b)
+        assert (a - bs * c) % N == 0, (c, a, bs)
+    assert n_ok >= len(cases) - 110  # the window budget is missed only by pathological c (the 100 N / small cases)
+
+
+def test_verify_half_size_equals_full_size(lib, tabs):
+    """the half-size predicate gives the reference's verdict on the whole curve: valid and corrupted signatures,
+    keys / nonce points with an 8-torsion component, identity and small-order keys"""
+    import ctypes
+    rnd = random.Random(22)
+    fo = ctypes.c_int(0)
+    tors = V.torsion_points()
+    def both(pk, u, Rp, c):
+        args = [H.ptr(H.pt_mont(pk)), H.ptr(H.limbs(u)), H.ptr(H.pt_mont(Rp)), H.ptr(H.limbs(c)), 1, H.ptr(tabs[0])]
+        slow = lib.h_verify_ec(*args, 0, ctypes.byref(fo))
+        fast = lib.h_verify_ec(*args, 1, ctypes.byref(fo))
+        assert fo.value == 1
+        return slow, fast
+    for trial in range(10):
+        sk, nonce, m = rnd.randrange(R), rnd.randrange(R), rnd.randrange(Q)
+        u, Rp, c = o.sign(sk, nonce, m, mul=V.mul)
+        pk = V.mul(o.G, sk)
+        assert both(pk, u, Rp, c) == (1, 1)
+        assert both(pk, (u + 1) % R, Rp, c) == (0, 0)
+        assert both(pk, u, o.pt_add(Rp, o.G), c) == (0, 0)
+        # torsion: PK' = PK + T, R' = R + c T verifies under the reference's equation (exact integer multiples)
+        T = tors[trial % len(tors)]
+        pkt = o.pt_add(pk, T)
+        Rt = o.pt_add(Rp, V.mul(T, c))
+        exp = int(o.pt_add(V.mul(o.G, u), V.mul(pkt, c)) == Rt)
+        assert exp == 1 and both(pkt, u, Rt, c) == (1, 1)
+        # ... and R' = R + c T + (another torsion point) does not
+        T2 = tors[(trial + 3) % len(tors)]
+        if T2 != o.IDENTITY:
+            assert both(pkt, u, o.pt_add(Rt, T2), c) == (0, 0)
+        # small-order key alone: accepts iff u G + c T == R
+        Rs = o.pt_add(V.mul(o.G, u), V.mul(T, c))
+        assert both(T, u, Rs, c) == (1, 1)

@@ -240,6 +240,7 @@ def main():
     w("// q = BLS12-381 scalar field (dusk_bls12_381::BlsScalar); r = JubJub scalar field (dusk_jubjub::JubJubScalar)")
     w("#define SB200_FQ_MOD_INIT %s" % fmt(Q))
     w("#define SB200_FR_MOD_INIT %s" % fmt(R))
+    w("#define SB200_8R_INIT %s   // 8 r = the order of the whole curve group (cofactor 8)" % fmt(8 * R))
     w("#define SB200_FQ_ONE_INIT %s   // 2^256 mod q" % fmt(RADIX % Q))
     w("#define SB200_FQ_R2_INIT %s    // 2^512 mod q" % fmt(RADIX * RADIX % Q))
     w("#define SB200_FR_R2_INIT %s    // 2^512 mod r" % fmt(RADIX * RADIX % R))

@@ -63,7 +63,7 @@ out["verify_vargen_affine"] = measure(lambda: lib.h_verify_vargen(H.ptr(H.pt_mon
 st = np.concatenate([H.mont(x) for x in range(5)])
 out["hades_perm_sparse"] = measure(lambda: lib.h_hades(H.ptr(st), 0))
 out["hades_perm_dense"] = measure(lambda: lib.h_hades(H.ptr(st), 1))
-out["_note"] = "counted by the instrumented host build of schnorr_b200/csrc (same per-tuple code as the kernels, 16-bit comb); 1 fq_mul = 120 IMAD.WIDE, 1 fq_sqr = 84, 1 fq_dot5 (5 products, 1 reduction) = 368, 1 fr_mont_mul = 128"
+out["_note"] = "counted by the instrumented host build of schnorr_b200/csrc (same per-tuple code as the kernels, 16-bit comb); 1 fq_mul = 120 IMAD.WIDE, 1 fq_sqr = 84, 1 fq_dot5 (5 products, 1 reduction) = 368, 1 fr_mont_mul = 128; single-key verify also counts the 13 limb products of every step of the half-size-scalar Euclid (hgcd.cuh)"
 if "--check" not in sys.argv:
     path = os.path.join(ROOT, "profiles", "op_counts.json")
     old = json.load(open(path)) if os.path.exists(path) else {}
