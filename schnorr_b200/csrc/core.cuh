@@ -97,38 +97,56 @@ SB_HD point_in point_neg(const point_in& p) {
   r.U = fq_neg(p.U);
   return r;
 }
-SB_HD bool verify_ec_core_fast(const point_in& PK, const uint32_t* u_in, const point_in& R, const uint32_t* c_in,
-                               const uint32_t* combG, bool& fast_ok) {
-  bool ok = scalar_lt_r(u_in);
-  hgcd_res h = half_gcd_8r(c_in);
-  fast_ok = h.ok;
+// shared part: the short vector (a, b) for the challenge and  w = b u mod r
+struct half_scalars {
+  hgcd_res h;      // a, |b| (offset-recoded for 4-bit windows), sign of b, ok
+  uint32_t w[8];   // b u mod r, offset-recoded for the comb
+};
+SB_HD half_scalars half_scalars_prepare(const uint32_t* u, const uint32_t* c_in) {
+  half_scalars hs;
+  hs.h = half_gcd_8r(c_in);
   fr bb, uu;
 #pragma unroll
   for (int i = 0; i < 8; i++) {
-    bb.v[i] = h.b[i];
-    uu.v[i] = ok ? u_in[i] : 0u;
+    bb.v[i] = hs.h.b[i];
+    uu.v[i] = u[i];
   }
   fr w = fr_mul(bb, uu);  // |b| u mod r
-  if (h.bneg) {           // b u = -(|b| u)
+  if (hs.h.bneg) {        // b u = -(|b| u)
     fr z;
 #pragma unroll
     for (int i = 0; i < 8; i++) z.v[i] = 0;
     w = fr_sub(z, w);
   }
+#pragma unroll
+  for (int i = 0; i < 8; i++) hs.w[i] = w.v[i];
+  recode_offset<4>(hs.h.a);
+  recode_offset<4>(hs.h.b);
+  recode_offset<COMB_BITS>(hs.w);
+  return hs;
+}
+// (b u) B + a PK - b R == identity  for the generator B whose comb table is `comb`
+SB_HD bool verify_ec_half(const point_in& PK, const point_in& R, const half_scalars& hs, const uint32_t* comb) {
   pniels tabs[2][9];  // [0]: multiples of -sign(b) R (|b| of them make -b R), [1]: multiples of PK
-  pniels *tabR = tabs[0], *tabP = tabs[1];
   {
-    const point_in nR = h.bneg ? R : point_neg(R);
+    const point_in nR = hs.h.bneg ? R : point_neg(R);
 #pragma unroll 1
     for (int t = 0; t < 2; t++) vartable_build(tabs[t], point_to_ext(t ? PK : nR));  // one copy of the table code
   }
-  recode_offset<4>(h.a);
-  recode_offset<4>(h.b);
-  p1p1 cp = ed_mul_var2_rolled(tabR, h.b, tabP, h.a, 34);
-  recode_offset<COMB_BITS>(w.v);
-  cp = ed_comb_add(p1p1_to_ext(cp), combG, w.v);
+  p1p1 cp = ed_mul_var2_rolled(tabs[0], hs.h.b, tabs[1], hs.h.a, 34);
+  cp = ed_comb_add(p1p1_to_ext(cp), comb, hs.w);
   // identity <=> X = E F = 0 and Y = G H = Z = F G with F, G != 0 (complete addition) <=> E = 0 and H = F
-  return ok & fq_is_zero(cp.E) & fq_eq(cp.H, cp.F);
+  return fq_is_zero(cp.E) & fq_eq(cp.H, cp.F);
+}
+SB_HD bool verify_ec_core_fast(const point_in& PK, const uint32_t* u_in, const point_in& R, const uint32_t* c_in,
+                               const uint32_t* combG, bool& fast_ok) {
+  bool ok = scalar_lt_r(u_in);
+  uint32_t u[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) u[i] = ok ? u_in[i] : 0u;
+  half_scalars hs = half_scalars_prepare(u, c_in);
+  fast_ok = hs.h.ok;
+  return ok & verify_ec_half(PK, R, hs, combG);
 }
 
 #ifndef SB_VERIFY_HGCD
@@ -189,12 +207,8 @@ SB_HD bool verify_vargen_core(const point_in& PK, const point_in& GEN, const uin
   return ok & p1p1_equals(cp, R);
 }
 
-#ifndef SB_DOUBLE_ROLL
-#define SB_DOUBLE_ROLL 1
-#endif
-SB_HD bool verify_double_core(const point_in& PK, const point_in& PKp, const uint32_t* u_in, const point_in& R,
-                              const point_in& Rp, const fq& m, const uint32_t* combG, const uint32_t* combGp,
-                              uint32_t* c_out) {
+// hash half of the double-key verification: c = H(R, R', m)
+SB_HD void verify_double_hash_core(const point_in& R, const point_in& Rp, const fq& m, uint32_t* c_out) {
   fq ru, rv, rpu, rpv;
   if (R.affine) {
     ru = R.U; rv = R.V; rpu = Rp.U; rpv = Rp.V;
@@ -205,17 +219,20 @@ SB_HD bool verify_double_core(const point_in& PK, const point_in& PKp, const uin
     ru = fq_mul(R.U, zi1); rv = fq_mul(R.V, zi1);
     rpu = fq_mul(Rp.U, zi2); rpv = fq_mul(Rp.V, zi2);
   }
-  uint32_t c[8];
-  chal5(ru, rv, rpu, rpv, m, c);
-#pragma unroll
-  for (int i = 0; i < 8; i++) c_out[i] = c[i];
+  chal5(ru, rv, rpu, rpv, m, c_out);
+}
+// curve half, full-size scalars: u G + c PK == R  and  u G' + c PK' == R'
+SB_HD bool verify_double_ec_core(const point_in& PK, const point_in& PKp, const uint32_t* u_in, const point_in& R,
+                                 const point_in& Rp, const uint32_t* c_in, const uint32_t* combG, const uint32_t* combGp) {
   bool ok = scalar_lt_r(u_in);
-  uint32_t u[8];
+  uint32_t u[8], c[8];
 #pragma unroll
-  for (int i = 0; i < 8; i++) u[i] = ok ? u_in[i] : 0u;
+  for (int i = 0; i < 8; i++) {
+    u[i] = ok ? u_in[i] : 0u;
+    c[i] = c_in[i];
+  }
   recode_offset<4>(c);
   recode_offset<COMB_BITS>(u);
-#if SB_DOUBLE_ROLL
   // the two key / nonce-point pairs run through ONE copy of the curve code (a 2-trip loop): two inlined copies double
   // the hot code and warps in different halves evict each other from the instruction cache
 #pragma unroll 1
@@ -228,18 +245,33 @@ SB_HD bool verify_double_core(const point_in& PK, const point_in& PKp, const uin
     cp = ed_comb_add(p1p1_to_ext(cp), k ? combGp : combG, u);
     ok &= p1p1_equals(cp, rr);
   }
-#else
-  pniels tab[9];
-  vartable_build(tab, point_to_ext(PK));
-  p1p1 cp = ed_mul_var(tab, c, 63);
-  cp = ed_comb_add(p1p1_to_ext(cp), combG, u);
-  ok &= p1p1_equals(cp, R);
-  vartable_build(tab, point_to_ext(PKp));
-  cp = ed_mul_var(tab, c, 63);
-  cp = ed_comb_add(p1p1_to_ext(cp), combGp, u);
-  ok &= p1p1_equals(cp, Rp);
-#endif
   return ok;
+}
+// ... with half-size scalars where they fit (one short vector serves both equations: same c, same u)
+SB_HD bool verify_double_ec(const point_in& PK, const point_in& PKp, const uint32_t* u_in, const point_in& R, const point_in& Rp,
+                            const uint32_t* c_in, const uint32_t* combG, const uint32_t* combGp) {
+#if SB_VERIFY_HGCD
+  bool ok = scalar_lt_r(u_in);
+  uint32_t u[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) u[i] = ok ? u_in[i] : 0u;
+  half_scalars hs = half_scalars_prepare(u, c_in);
+#pragma unroll 1
+  for (int k = 0; k < 2; k++) ok &= verify_ec_half(k ? PKp : PK, k ? Rp : R, hs, k ? combGp : combG);
+  if (SB_WARP_ANY(!hs.h.ok)) {
+    bool slow = verify_double_ec_core(PK, PKp, u_in, R, Rp, c_in, combG, combGp);
+    ok = hs.h.ok ? ok : slow;
+  }
+  return ok;
+#else
+  return verify_double_ec_core(PK, PKp, u_in, R, Rp, c_in, combG, combGp);
+#endif
+}
+SB_HD bool verify_double_core(const point_in& PK, const point_in& PKp, const uint32_t* u_in, const point_in& R,
+                              const point_in& Rp, const fq& m, const uint32_t* combG, const uint32_t* combGp,
+                              uint32_t* c_out) {
+  verify_double_hash_core(R, Rp, m, c_out);
+  return verify_double_ec(PK, PKp, u_in, R, Rp, c_out, combG, combGp);
 }
 
 SB_HD void ext_to_affine(const ext& p, fq& u, fq& v) {

@@ -32,7 +32,7 @@ constexpr int TPB = 128;
 #ifndef SB_VERIFY_CTAS
 #define SB_VERIFY_CTAS SB_MIN_CTAS
 #endif
-constexpr int min_ctas(int op) { return (op == 0 || op == 19) ? SB_VERIFY_CTAS : (op == 1 || op == 2) ? SB_MIN_CTAS - 1 : SB_MIN_CTAS; }
+constexpr int min_ctas(int op) { return (op == 0 || op == 19) ? SB_VERIFY_CTAS : op == 25 ? SB_MIN_CTAS - 1 : (op == 1 || op == 2) ? SB_MIN_CTAS - 1 : SB_MIN_CTAS; }
 constexpr int MAX_IN = 6, MAX_OUT = 4;
 constexpr int64_t CHUNK = 1 << 18;  // tuples per pipeline stage
 
@@ -40,7 +40,8 @@ enum Op : int {
   OP_VERIFY = 0, OP_VERIFY_DOUBLE, OP_VERIFY_VARGEN, OP_SIGN, OP_SIGN_DOUBLE, OP_SIGN_VARGEN,
   OP_KEYGEN, OP_KEYGEN_DOUBLE, OP_KEYGEN_VARGEN, OP_DBG_FQ, OP_DBG_FR_MUL, OP_DBG_HADES, OP_DBG_SMUL,
   OP_DECOMPRESS, OP_COMPRESS, OP_FROM_WIDE, OP_VERIFY_BYTES, OP_SIGN_BYTES, OP_CHALLENGE, OP_VERIFY_EC,
-  OP_VERIFY_DOUBLE_BYTES, OP_VERIFY_VARGEN_BYTES, OP_SIGN_DOUBLE_BYTES, OP_SIGN_VARGEN_BYTES
+  OP_VERIFY_DOUBLE_BYTES, OP_VERIFY_VARGEN_BYTES, OP_SIGN_DOUBLE_BYTES, OP_SIGN_VARGEN_BYTES,
+  OP_CHALLENGE_DOUBLE, OP_VERIFY_DOUBLE_EC
 };
 
 struct KArgs {
@@ -137,6 +138,22 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
     ldg_scalar(a.in[1] + i * 8, u);
     ldg_scalar(a.out[0] + i * 8, c);
     bool ok = verify_ec(ldg_point(a.in[0], i, aff), u, ldg_point(a.in[2], i, aff), c, a.combG);
+    unsigned word = __ballot_sync(0xffffffffu, ok && active);
+    if ((threadIdx.x & 31) == 0 && active) a.bitmap[i >> 5] = word;
+    return;
+  }
+
+  if (OP == OP_CHALLENGE_DOUBLE) {  // in: -, -, -, R, R', m -> out0: c
+    verify_double_hash_core(ldg_point(a.in[3], i, aff), ldg_point(a.in[4], i, aff), ldg_fq(a.in[5] + i * 8), c);
+    if (active) stg8(a.out[0] + i * 8, c);
+    return;
+  }
+  if (OP == OP_VERIFY_DOUBLE_EC) {  // in: pk, pk', u, R, R', - ; out0 (as input): c -> bitmap
+    uint32_t u[8];
+    ldg_scalar(a.in[2] + i * 8, u);
+    ldg_scalar(a.out[0] + i * 8, c);
+    bool ok = verify_double_ec(ldg_point(a.in[0], i, aff), ldg_point(a.in[1], i, aff), u, ldg_point(a.in[3], i, aff),
+                               ldg_point(a.in[4], i, aff), c, a.combG, a.combGp);
     unsigned word = __ballot_sync(0xffffffffu, ok && active);
     if ((threadIdx.x & 31) == 0 && active) a.bitmap[i >> 5] = word;
     return;
@@ -604,6 +621,13 @@ int launch(sb200_ctx* ctx, Op op, const KArgs& a, cudaStream_t st) {
     CU(cudaGetLastError());
     return SB200_OK;
   }
+  if (op == OP_VERIFY_DOUBLE) {
+    k_run<OP_CHALLENGE_DOUBLE><<<grid, TPB, 0, st>>>(a);
+    k_run<OP_VERIFY_DOUBLE_EC><<<grid, TPB, 0, st>>>(a);
+    ctx->launches.fetch_add(2, std::memory_order_relaxed);
+    CU(cudaGetLastError());
+    return SB200_OK;
+  }
 #endif
   switch (op) {
 #define CASEK(O) case O: k_fixed_batch<O><<<gridk(O), TPB, 0, st>>>(a); break;
@@ -641,7 +665,7 @@ int run(sb200_ctx* ctx, int64_t n, const Desc& d) {
     for (int k = 0; k < d.nin; k++) a.in[k] = d.in[k];
     for (int k = 0; k < d.nout; k++) a.out[k] = d.out[k];
 #if SB_VERIFY_SPLIT
-    if (d.op == OP_VERIFY && !(d.flags & SB200_VERIFY_DUAL_PIPE) && !a.out[0]) {  // hash and curve kernels hand c over in memory
+    if (((d.op == OP_VERIFY && !(d.flags & SB200_VERIFY_DUAL_PIPE)) || d.op == OP_VERIFY_DOUBLE) && !a.out[0]) {  // hash and curve kernels hand c over in memory
       size_t need = (size_t)n * 32;
       if (dc.cscratch_cap < need) {
         CU(cudaStreamSynchronize(ctx->user_stream));
@@ -660,7 +684,7 @@ int run(sb200_ctx* ctx, int64_t n, const Desc& d) {
   size_t per_tuple = 0;
   for (int k = 0; k < d.nin; k++) per_tuple += (size_t)d.in_words[k] * 4;
   for (int k = 0; k < d.nout; k++) per_tuple += (d.out[k] && d.out_words[k] > 0) ? (size_t)d.out_words[k] * 4 : 0;
-  const bool c_scratch = SB_VERIFY_SPLIT && d.op == OP_VERIFY && !d.out[0];  // device-only challenge rows between the two kernels
+  const bool c_scratch = SB_VERIFY_SPLIT && (d.op == OP_VERIFY || d.op == OP_VERIFY_DOUBLE) && !d.out[0];  // device-only challenge rows between the two kernels
   if (c_scratch) per_tuple += 32;
 
   const int ndev = (int)ctx->devs.size();
