@@ -186,25 +186,29 @@ SB_HD bool verify_core(const point_in& PK, const uint32_t* u_in, const point_in&
   return verify_ec(PK, u_in, R, c_out, combG);
 }
 
-SB_HD bool verify_vargen_core(const point_in& PK, const point_in& GEN, const uint32_t* u_in, const point_in& R,
-                              const fq& m, uint32_t* c_out) {
-  fq ru, rv;
-  point_to_affine(R, ru, rv);
-  uint32_t c[8];
-  chal3(ru, rv, m, c);
-#pragma unroll
-  for (int i = 0; i < 8; i++) c_out[i] = c[i];
+// curve half of the variable-generator verification: u Gen + c PK == R (Straus, both bases variable; the half-size
+// trick does not apply: the generator's scalar b u mod r would be full-size again)
+SB_HD bool verify_vargen_ec(const point_in& PK, const point_in& GEN, const uint32_t* u_in, const point_in& R,
+                            const uint32_t* c_in) {
   bool ok = scalar_lt_r(u_in);
-  uint32_t u[8];
+  uint32_t u[8], c[8];
 #pragma unroll
-  for (int i = 0; i < 8; i++) u[i] = ok ? u_in[i] : 0u;
-  pniels tabG[9], tabP[9];
-  vartable_build(tabG, point_to_ext(GEN));
-  vartable_build(tabP, point_to_ext(PK));
+  for (int i = 0; i < 8; i++) {
+    u[i] = ok ? u_in[i] : 0u;
+    c[i] = c_in[i];
+  }
+  pniels tabs[2][9];
+#pragma unroll 1
+  for (int t = 0; t < 2; t++) vartable_build(tabs[t], point_to_ext(t ? PK : GEN));
   recode_offset<4>(c);
   recode_offset<4>(u);
-  p1p1 cp = ed_mul_var2(tabG, u, tabP, c, 64);
+  p1p1 cp = ed_mul_var2_rolled(tabs[0], u, tabs[1], c, 64);
   return ok & p1p1_equals(cp, R);
+}
+SB_HD bool verify_vargen_core(const point_in& PK, const point_in& GEN, const uint32_t* u_in, const point_in& R,
+                              const fq& m, uint32_t* c_out) {
+  verify_hash_core(R, m, c_out);
+  return verify_vargen_ec(PK, GEN, u_in, R, c_out);
 }
 
 // hash half of the double-key verification: c = H(R, R', m)

@@ -32,7 +32,7 @@ constexpr int TPB = 128;
 #ifndef SB_VERIFY_CTAS
 #define SB_VERIFY_CTAS SB_MIN_CTAS
 #endif
-constexpr int min_ctas(int op) { return (op == 0 || op == 19) ? SB_VERIFY_CTAS : op == 25 ? SB_MIN_CTAS - 1 : (op == 1 || op == 2) ? SB_MIN_CTAS - 1 : SB_MIN_CTAS; }
+constexpr int min_ctas(int op) { return (op == 0 || op == 19) ? SB_VERIFY_CTAS : (op == 25 || op == 27) ? SB_MIN_CTAS - 1 : (op == 1 || op == 2) ? SB_MIN_CTAS - 1 : SB_MIN_CTAS; }
 constexpr int MAX_IN = 6, MAX_OUT = 4;
 constexpr int64_t CHUNK = 1 << 18;  // tuples per pipeline stage
 
@@ -41,7 +41,7 @@ enum Op : int {
   OP_KEYGEN, OP_KEYGEN_DOUBLE, OP_KEYGEN_VARGEN, OP_DBG_FQ, OP_DBG_FR_MUL, OP_DBG_HADES, OP_DBG_SMUL,
   OP_DECOMPRESS, OP_COMPRESS, OP_FROM_WIDE, OP_VERIFY_BYTES, OP_SIGN_BYTES, OP_CHALLENGE, OP_VERIFY_EC,
   OP_VERIFY_DOUBLE_BYTES, OP_VERIFY_VARGEN_BYTES, OP_SIGN_DOUBLE_BYTES, OP_SIGN_VARGEN_BYTES,
-  OP_CHALLENGE_DOUBLE, OP_VERIFY_DOUBLE_EC
+  OP_CHALLENGE_DOUBLE, OP_VERIFY_DOUBLE_EC, OP_CHALLENGE_VARGEN, OP_VERIFY_VARGEN_EC
 };
 
 struct KArgs {
@@ -143,6 +143,20 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
     return;
   }
 
+  if (OP == OP_CHALLENGE_VARGEN) {  // in: -, -, -, R, m -> out0: c
+    verify_hash_core(ldg_point(a.in[3], i, aff), ldg_fq(a.in[4] + i * 8), c);
+    if (active) stg8(a.out[0] + i * 8, c);
+    return;
+  }
+  if (OP == OP_VERIFY_VARGEN_EC) {  // in: pk, gen, u, R, - ; out0 (as input): c -> bitmap
+    uint32_t u[8];
+    ldg_scalar(a.in[2] + i * 8, u);
+    ldg_scalar(a.out[0] + i * 8, c);
+    bool ok = verify_vargen_ec(ldg_point(a.in[0], i, aff), ldg_point(a.in[1], i, aff), u, ldg_point(a.in[3], i, aff), c);
+    unsigned word = __ballot_sync(0xffffffffu, ok && active);
+    if ((threadIdx.x & 31) == 0 && active) a.bitmap[i >> 5] = word;
+    return;
+  }
   if (OP == OP_CHALLENGE_DOUBLE) {  // in: -, -, -, R, R', m -> out0: c
     verify_double_hash_core(ldg_point(a.in[3], i, aff), ldg_point(a.in[4], i, aff), ldg_fq(a.in[5] + i * 8), c);
     if (active) stg8(a.out[0] + i * 8, c);
@@ -383,6 +397,9 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
 #ifndef SB_VERIFY_WS
 #define SB_VERIFY_WS 1
 #endif
+#ifndef SB_VARGEN_SPLIT
+#define SB_VARGEN_SPLIT 1
+#endif
 #ifndef SB_VERIFY_SPLIT
 #define SB_VERIFY_SPLIT 1  // hash and curve halves as two launches: with the half-size curve path the single kernel's phases evict each other from the instruction cache (21.1 -> 22.9 M verifies/s)
 #endif
@@ -621,6 +638,15 @@ int launch(sb200_ctx* ctx, Op op, const KArgs& a, cudaStream_t st) {
     CU(cudaGetLastError());
     return SB200_OK;
   }
+#if SB_VARGEN_SPLIT
+  if (op == OP_VERIFY_VARGEN) {
+    k_run<OP_CHALLENGE_VARGEN><<<grid, TPB, 0, st>>>(a);
+    k_run<OP_VERIFY_VARGEN_EC><<<grid, TPB, 0, st>>>(a);
+    ctx->launches.fetch_add(2, std::memory_order_relaxed);
+    CU(cudaGetLastError());
+    return SB200_OK;
+  }
+#endif
   if (op == OP_VERIFY_DOUBLE) {
     k_run<OP_CHALLENGE_DOUBLE><<<grid, TPB, 0, st>>>(a);
     k_run<OP_VERIFY_DOUBLE_EC><<<grid, TPB, 0, st>>>(a);
@@ -665,7 +691,7 @@ int run(sb200_ctx* ctx, int64_t n, const Desc& d) {
     for (int k = 0; k < d.nin; k++) a.in[k] = d.in[k];
     for (int k = 0; k < d.nout; k++) a.out[k] = d.out[k];
 #if SB_VERIFY_SPLIT
-    if (((d.op == OP_VERIFY && !(d.flags & SB200_VERIFY_DUAL_PIPE)) || d.op == OP_VERIFY_DOUBLE) && !a.out[0]) {  // hash and curve kernels hand c over in memory
+    if (((d.op == OP_VERIFY && !(d.flags & SB200_VERIFY_DUAL_PIPE)) || d.op == OP_VERIFY_DOUBLE || (SB_VARGEN_SPLIT && d.op == OP_VERIFY_VARGEN)) && !a.out[0]) {  // hash and curve kernels hand c over in memory
       size_t need = (size_t)n * 32;
       if (dc.cscratch_cap < need) {
         CU(cudaStreamSynchronize(ctx->user_stream));
@@ -684,7 +710,7 @@ int run(sb200_ctx* ctx, int64_t n, const Desc& d) {
   size_t per_tuple = 0;
   for (int k = 0; k < d.nin; k++) per_tuple += (size_t)d.in_words[k] * 4;
   for (int k = 0; k < d.nout; k++) per_tuple += (d.out[k] && d.out_words[k] > 0) ? (size_t)d.out_words[k] * 4 : 0;
-  const bool c_scratch = SB_VERIFY_SPLIT && (d.op == OP_VERIFY || d.op == OP_VERIFY_DOUBLE) && !d.out[0];  // device-only challenge rows between the two kernels
+  const bool c_scratch = SB_VERIFY_SPLIT && (d.op == OP_VERIFY || d.op == OP_VERIFY_DOUBLE || (SB_VARGEN_SPLIT && d.op == OP_VERIFY_VARGEN)) && !d.out[0];  // device-only challenge rows between the two kernels
   if (c_scratch) per_tuple += 32;
 
   const int ndev = (int)ctx->devs.size();
