@@ -55,6 +55,7 @@ struct KArgs {
   const uint32_t* combGp;
   struct WsState* ws;
   int nsm;
+  pniels* ec_scratch;  // window tables of k_verify_ec_p: EC_P_CTAS * nsm * TPB threads x 18 entries (per stream)
 };
 
 // scheduling state of one warp-specialised launch (k_verify_ws): the next-tile counter, reset before every launch,
@@ -483,6 +484,30 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_verify_ws(const KArgs a) {
   }
 }
 
+// Curve half of the single-key verification as a persistent kernel whose window tables live in a thread-major global
+// scratch region (18 entries x 128 B per resident thread) instead of local memory: see verify_ec_half.
+#ifndef SB_EC_GLOBAL_TABLES
+#define SB_EC_GLOBAL_TABLES 0  // measured: DRAM traffic 188 -> 32 GB per 2^22 launch, but the curve kernel takes 149 ms instead of 125 (L1 serves local memory write-back, global stores go through to L2): 20.4 vs 23.0 M verifies/s
+#endif
+constexpr int EC_P_CTAS = 4;
+__global__ void __launch_bounds__(TPB, EC_P_CTAS) k_verify_ec_p(const KArgs a, pniels* scratch) {
+  const bool aff = (a.flags & SB200_POINTS_AFFINE) != 0;
+  pniels* store = scratch + ((size_t)blockIdx.x * TPB + threadIdx.x) * 18;
+  const int64_t ntiles = (a.n + TPB - 1) / TPB;
+#pragma unroll 1
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int64_t i = tile * TPB + threadIdx.x;
+    const bool active = i < a.n;
+    if (!active) i = a.n - 1;
+    uint32_t u[8], c[8];
+    ldg_scalar(a.in[1] + i * 8, u);
+    ldg_scalar(a.out[0] + i * 8, c);
+    bool ok = verify_ec<true>(ldg_point(a.in[0], i, aff), u, ldg_point(a.in[2], i, aff), c, a.combG, store);
+    unsigned word = __ballot_sync(0xffffffffu, ok && active);
+    if ((threadIdx.x & 31) == 0 && active) a.bitmap[i >> 5] = word;
+  }
+}
+
 // Fixed-base signing / key generation with several tuples per thread: the scalar multiples of G (and G') are
 // computed first, all their Z coordinates are inverted together (one field inversion per thread instead of one
 // per point: the inversion is a third of a single signature's work), then each tuple is finished.
@@ -577,6 +602,7 @@ struct DevCtx {
   uint8_t* arena[2] = {nullptr, nullptr};
   size_t arena_cap[2] = {0, 0};
   WsState* ws[3] = {nullptr, nullptr, nullptr};  // per pipeline stream, [2] = caller's stream (SB200_DEVICE_PTRS)
+  pniels* ec_scratch[3] = {nullptr, nullptr, nullptr};  // k_verify_ec_p window tables, per stream like ws
   uint32_t* cscratch = nullptr;                  // challenges of a SB200_DEVICE_PTRS verify call without c_out
   size_t cscratch_cap = 0;
   int nsm = 0;
@@ -633,7 +659,11 @@ int launch(sb200_ctx* ctx, Op op, const KArgs& a, cudaStream_t st) {
 #if SB_VERIFY_SPLIT
   if (op == OP_VERIFY) {  // a.out[0] is always set here: the caller's c_out or scratch
     k_run<OP_CHALLENGE><<<grid, TPB, 0, st>>>(a);
+#if SB_EC_GLOBAL_TABLES
+    k_verify_ec_p<<<std::min<unsigned>(grid, (unsigned)(EC_P_CTAS * a.nsm)), TPB, 0, st>>>(a, a.ec_scratch);
+#else
     k_run<OP_VERIFY_EC><<<grid, TPB, 0, st>>>(a);
+#endif
     ctx->launches.fetch_add(2, std::memory_order_relaxed);
     CU(cudaGetLastError());
     return SB200_OK;
@@ -687,7 +717,7 @@ int run(sb200_ctx* ctx, int64_t n, const Desc& d) {
     CU(cudaSetDevice(dc.dev));
     KArgs a{};
     a.n = n; a.flags = d.flags; a.aux = d.aux; a.combG = dc.combG; a.combGp = dc.combGp; a.bitmap = d.bitmap;
-    a.ws = dc.ws[2]; a.nsm = dc.nsm;
+    a.ws = dc.ws[2]; a.nsm = dc.nsm; a.ec_scratch = dc.ec_scratch[2];
     for (int k = 0; k < d.nin; k++) a.in[k] = d.in[k];
     for (int k = 0; k < d.nout; k++) a.out[k] = d.out[k];
 #if SB_VERIFY_SPLIT
@@ -737,7 +767,7 @@ int run(sb200_ctx* ctx, int64_t n, const Desc& d) {
       auto carve = [&](size_t bytes) { uint8_t* r = p; p += (bytes + 63) & ~(size_t)63; return r; };
       KArgs a{};
       a.n = cn; a.flags = d.flags; a.aux = d.aux; a.combG = dc.combG; a.combGp = dc.combGp;
-      a.ws = dc.ws[slot]; a.nsm = dc.nsm;
+      a.ws = dc.ws[slot]; a.nsm = dc.nsm; a.ec_scratch = dc.ec_scratch[slot];
       for (int k = 0; k < d.nin; k++) {
         if (!d.in_words[k]) continue;
         size_t bytes = (size_t)cn * d.in_words[k] * 4;
@@ -803,6 +833,10 @@ int sb200_init(const int* devices, int n_devices, sb200_ctx** out) {
     for (int s = 0; s < 3; s++)
       if (cudaMalloc(&dc.ws[s], sizeof(WsState)) != cudaSuccess || cudaMemset(dc.ws[s], 0, sizeof(WsState)) != cudaSuccess)
         return fail(SB200_ERR_NOMEM);
+#if SB_EC_GLOBAL_TABLES
+    for (int s = 0; s < 3; s++)  // 4 x 148 x 128 threads x 2 304 B = 175 MB per stream
+      if (cudaMalloc(&dc.ec_scratch[s], (size_t)EC_P_CTAS * dc.nsm * TPB * 18 * sizeof(pniels)) != cudaSuccess) return fail(SB200_ERR_NOMEM);
+#endif
     ctx->devs.push_back(dc);
     int grid = (COMB_WINDOWS * COMB_ENTRIES + TPB - 1) / TPB;
     k_comb_build<<<grid, TPB, 0, dc.stream[0]>>>(dc.combG, 0);
@@ -827,6 +861,8 @@ void sb200_destroy(sb200_ctx* ctx) {
     for (int s = 0; s < 3; s++)
       if (dc.ws[s]) cudaFree(dc.ws[s]);
     if (dc.cscratch) cudaFree(dc.cscratch);
+    for (int s = 0; s < 3; s++)
+      if (dc.ec_scratch[s]) cudaFree(dc.ec_scratch[s]);
   }
   delete ctx;
 }
