@@ -24,6 +24,9 @@ using namespace sb200;
 namespace {
 
 constexpr int TPB = 128;
+#ifndef SB_CHALLENGE_FD
+#define SB_CHALLENGE_FD 0  // the stand-alone challenge kernel on the FP64 pipe instead of IMAD.WIDE: measured equal (182.94 vs 182.91 ms per 2^22 verifications)
+#endif
 #ifndef SB_MIN_CTAS
 #define SB_MIN_CTAS 4
 #endif
@@ -130,7 +133,15 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
   // single-key verification as two launches (SB_VERIFY_SPLIT): all warps of an SM are then in the same phase, and each
   // phase's code (hash: 26 KB, curve: 19 KB) fits the 32 KB L1.5 instruction cache by itself
   if (OP == OP_CHALLENGE) {  // in: -, -, R, m -> out0: c
+#if SB_CHALLENGE_FD
+    {  // the challenge kernel on the FP64 pipe (hades_fd.cuh): nothing else competes for issue slots here
+      fq ru, rv;
+      point_to_affine(ldg_point(a.in[2], i, aff), ru, rv);
+      challenge3_fd(ru, rv, ldg_fq(a.in[3] + i * 8), c);
+    }
+#else
     verify_hash_core(ldg_point(a.in[2], i, aff), ldg_fq(a.in[3] + i * 8), c);
+#endif
     if (active) stg8(a.out[0] + i * 8, c);
     return;
   }
