@@ -178,6 +178,14 @@ def test_ragged_batch_across_pipeline_chunks(engine, dual_pipe):
     s0 = n - m
     okp, cp = engine.verify(scale(pk[s0:]), u[s0:], scale(R_[s0:]), msg[s0:], affine=False, dual_pipe=dual_pipe)
     assert (okp == ok[s0:]).all() and (cp == c[s0:]).all()
+    # without c_out the challenges travel between the two kernels in device scratch only
+    ok3, none = engine.verify(pk, u, R_, msg, want_c=False, dual_pipe=dual_pipe)
+    assert none is None and (ok3 == ok).all()
+    pkd, pkdp = engine.keygen_double(sk[:m])
+    ud, Rd, Rdp, cd = engine.sign_double(sk[:m], msg[:m], nonce[:m])
+    okd, _ = engine.verify_double(pkd, pkdp, ud, Rd, Rdp, msg[:m], want_c=False)
+    okv, _ = engine.verify_vargen(pk[:m], pkd, ud, Rd, msg[:m], want_c=False)  # generator = G-keys: u Gen + c PK != R in general
+    assert okd.all() and not okv.all()
 
 
 def test_config2_double_verify_2_20_properties(engine):
