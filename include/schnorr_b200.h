@@ -51,10 +51,14 @@ typedef struct sb200_ctx sb200_ctx;
 
 enum {
   SB200_OK = 0,
-  SB200_ERR_ARG = -1,   /* null pointer, n < 0, unknown flag, misaligned buffer */
-  SB200_ERR_CUDA = -2,  /* a CUDA call failed; sb200_last_error() has the text */
-  SB200_ERR_NODEV = -3, /* no usable sm_100 device */
-  SB200_ERR_NOMEM = -4
+  SB200_ERR_ARG = -1,    /* null pointer, n < 0, unknown flag, misaligned buffer */
+  SB200_ERR_CUDA = -2,   /* a CUDA call failed; sb200_last_error() has the text */
+  SB200_ERR_NODEV = -3,  /* no usable sm_100 device */
+  SB200_ERR_NOMEM = -4,
+  SB200_ERR_PARAMS = -5, /* sb200_params rejected: generator off the curve / not of prime order, non-canonical field
+                            element, singular MDS block, or the sparse form failed its self-check */
+  SB200_ERR_BUSY = -6    /* a live context on the same device was created with different parameters (the Hades
+                            tables live in that device's constant memory, one set per process and device) */
 };
 
 #define SB200_POINTS_PROJECTIVE 0u
@@ -62,22 +66,70 @@ enum {
 /* All buffers are device pointers on the context's (single) device; the call enqueues its kernel on
  * the stream set with sb200_set_stream and returns without synchronising. */
 #define SB200_DEVICE_PTRS 2u
-/* sb200_verify only: run the warp-specialised kernel (hash warps on the FP64 pipe beside curve warps on the
- * FMA-heavy pipe).  Same verdicts and challenges; measured at parity with the default kernel. */
+/* sb200_verify only, and only in builds with -DSB_EXPERIMENTAL_FD=1 (otherwise SB200_ERR_ARG): the warp-specialised
+ * kernel with hash warps on the FP64 pipe.  Same verdicts; measured 22 % slower than the default. */
 #define SB200_VERIFY_DUAL_PIPE 4u
+/* sb200_verify / _double / _vargen: additionally check every input point (on the curve, Z != 0) on the device; a
+ * tuple with a failing point gets verdict 0 instead of undefined behaviour.  For callers that build keys with
+ * `from_raw_unchecked` (/root/reference/src/keys/public.rs:142,256,427).  See also sb200_points_check. */
+#define SB200_CHECK_POINTS 8u
+
+/* ---- scheme parameters ------------------------------------------------------------------------------------------
+ * Everything numeric that dusk-schnorr takes from its un-vendored dependency crates and that cannot be checked in
+ * this build environment is an INPUT of context creation:
+ *   generator, generator_nums   dusk_jubjub::GENERATOR / GENERATOR_NUMS, affine (u, v)
+ *                               (GENERATOR_EXTENDED, GENERATOR_NUMS_EXTENDED at /root/reference/src/keys/secret.rs:159,231-232,
+ *                               /root/reference/src/keys/public.rs:63,127,236-239,267-268)
+ *   round_constants             dusk_hades ROUND_CONSTANTS[0 .. 335) (67 rounds x 5 words, consumed in order)
+ *   mds                         dusk_hades MDS_MATRIX[i][j]; a round computes result[i] = sum_j mds[i][j] * state[j]
+ *                               (both used by sponge::truncated::hash at /root/reference/src/signatures.rs:133,283-289)
+ * All field elements are 8 x u32 Montgomery limbs = the crate's own `BlsScalar.0`, so a Rust host copies its tables
+ * verbatim (rust/src/cuda.rs `params_from_crate`).  The sparse factorisation of the partial rounds that the kernels
+ * run is derived from these at sb200_init_ex and checked against the dense permutation before anything is uploaded. */
+typedef struct sb200_params {
+  uint32_t struct_size; /* = sizeof(sb200_params) */
+  uint32_t reserved;    /* 0 */
+  uint32_t generator[16];
+  uint32_t generator_nums[16];
+  uint32_t round_constants[335][8];
+  uint32_t mds[5][5][8];
+} sb200_params;
+
+/* Rules for the DEFAULT round constants.  Both are recollections of dusk-hades' published recipe (assets/HOWTO.md:
+ * bytes = "poseidon-for-plonk"; repeat bytes = SHA-512(bytes), h_i = BlsScalar::from_bytes_wide(bytes)); they differ in
+ * whether the table is the running sum seeded with one.  Which one the crate uses is unverifiable here
+ * (DESIGN.md section 2); rust/tests/dump_golden.rs settles it, and a host with the crate passes its own table. */
+#define SB200_ARK_CUMSUM 0 /* p = 1; c_i = h_i + p; p = c_i   (default) */
+#define SB200_ARK_PLAIN 1  /* c_i = h_i */
+#define SB200_ARK_ENV (-1) /* the rule named by the environment variable SB200_ARK ("cumsum" | "plain"), else CUMSUM */
+/* Fill *out with the default parameters: recalled generators, recipe-derived round constants, Cauchy MDS 1/(i+j+5).
+ * Host-only (no CUDA call). */
+int sb200_default_params(int ark_rule, sb200_params* out);
 
 /* devices: CUDA ordinals to shard over (tuples are split into contiguous blocks, multiples of 32);
- * n_devices = 0 means "device 0".  Builds the comb tables of G and G' on every device. */
+ * n_devices = 0 means "device 0".  Validates the parameters, derives and uploads the Hades tables and builds the comb
+ * tables of both generators on every device. */
+int sb200_init_ex(const sb200_params* params, const int* devices, int n_devices, sb200_ctx** out);
+/* = sb200_init_ex(sb200_default_params(SB200_ARK_ENV), ...) */
 int sb200_init(const int* devices, int n_devices, sb200_ctx** out);
+/* Validate parameters exactly as sb200_init_ex does, without touching a GPU: canonical field elements, both generators
+ * on the curve and of prime order r, the partial-round blocks invertible, sparse form == dense permutation.
+ * tables_out (nullable, 1039 x 8 u32) receives the derived Hades tables (layout of sb200_dbg_hades_tables). */
+int sb200_params_check(const sb200_params* params, uint32_t* tables_out);
+/* the parameters a context was created with */
+int sb200_get_params(const sb200_ctx* ctx, sb200_params* out);
 void sb200_destroy(sb200_ctx* ctx);
 const char* sb200_strerror(int code);
 const char* sb200_last_error(const sb200_ctx* ctx);
 int sb200_device_count(const sb200_ctx* ctx);
-/* stream (a cudaStream_t) used by SB200_DEVICE_PTRS calls; NULL = the legacy default stream */
+/* stream (a cudaStream_t) used by SB200_DEVICE_PTRS calls; NULL = the legacy default stream.  The split kernels of
+ * one context share a scratch buffer, so DEVICE_PTRS work of one context is ordered: after a switch, the new stream
+ * first waits (cudaStreamWaitEvent) for what the context enqueued on the previous one. */
 int sb200_set_stream(sb200_ctx* ctx, void* cuda_stream);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 uint64_t sb200_launch_count(const sb200_ctx* ctx);
-/* pinned host memory for full-speed host<->device copies (pageable memory also works, slower) */
+/* pinned host memory for full-speed host<->device copies.  Pageable buffers also work: the library detects them and
+ * stages every chunk through its own pinned ring, so the copy/compute overlap is kept (one extra host memcpy). */
 int sb200_host_alloc(size_t bytes, void** out);
 void sb200_host_free(void* p);
 
@@ -128,9 +180,12 @@ int sb200_fq_from_mont(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t
  * `invalid` may be NULL. */
 int sb200_verify_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* pk32, const uint8_t* sig64,
                        const uint8_t* msg32, uint32_t* verdicts, uint32_t* invalid);
-/* SecretKey::from_bytes(sk).sign(nonce, BlsScalar::from_bytes(msg)).to_bytes() for n tuples */
+/* SecretKey::from_bytes(sk)?.sign(nonce, BlsScalar::from_bytes(msg)?).to_bytes() for n tuples.
+ * All three byte-level signers: invalid bit i = 1 where a from_bytes of the reference would return Err(InvalidData)
+ * -- sk >= r, nonce >= r (JubJubScalar::from_bytes, /root/reference/src/keys/secret.rs:96-102), msg >= q, or (vargen)
+ * a generator that does not decode; that tuple's signature bytes are all zero.  `invalid` may be NULL. */
 int sb200_sign_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* sk32, const uint8_t* msg32,
-                     const uint8_t* nonce32, uint8_t* sig64_out);
+                     const uint8_t* nonce32, uint8_t* sig64_out, uint32_t* invalid);
 
 /* The same for the other two schemes:
  * pk64  = PublicKeyDouble::to_bytes = pk || pk'           /root/reference/src/keys/public.rs:282-299
@@ -144,10 +199,14 @@ int sb200_verify_vargen_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const u
                               const uint8_t* msg32, uint32_t* verdicts, uint32_t* invalid);
 /* SecretKey::from_bytes(sk).sign_double(nonce, msg).to_bytes() */
 int sb200_sign_double_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* sk32, const uint8_t* msg32,
-                            const uint8_t* nonce32, uint8_t* sig96_out);
-/* SecretKeyVarGen::from_bytes(sk64)?.sign(nonce, msg).to_bytes(); ok bit i = 0 where the generator does not decode */
+                            const uint8_t* nonce32, uint8_t* sig96_out, uint32_t* invalid);
+/* SecretKeyVarGen::from_bytes(sk64)?.sign(nonce, msg).to_bytes() */
 int sb200_sign_vargen_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* sk64, const uint8_t* msg32,
-                            const uint8_t* nonce32, uint8_t* sig64_out, uint32_t* ok_bitmap);
+                            const uint8_t* nonce32, uint8_t* sig64_out, uint32_t* invalid);
+
+/* on-curve and Z != 0 check of n points (what SB200_CHECK_POINTS applies inside the verify calls); ok bit i = 1 if
+ * point i is a well-formed curve point.  No subgroup check (the reference has none either). */
+int sb200_points_check(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* points, uint32_t* ok_bitmap);
 
 /* Building-block probes for the parity tests (same kernels' device functions, one element per thread).
  * op: 0 mul (Montgomery product), 1 add, 2 sub, 3 inverse (b ignored), 4 square, 5 to_mont, 6 from_mont */
@@ -160,6 +219,13 @@ int sb200_dbg_hades(sb200_ctx* ctx, int64_t n, int dense, uint32_t* states);  /*
 /* out[i] = k[i] * P[i] (affine); base: 0 = fixed G, 1 = fixed G', 2 = variable (points given) */
 int sb200_dbg_scalar_mul(sb200_ctx* ctx, int64_t n, uint32_t flags, int base, const uint32_t* points,
                          const uint32_t* k, uint32_t* out);
+/* the curve half of sb200_verify alone, with caller-supplied challenges c (n x 8 u32, any integer < 2^252): verdict
+ * i = (u G + c PK == R).  Lets a test drive the half-size-scalar path and its full-size fallback with chosen c. */
+int sb200_dbg_verify_ec(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* pk, const uint32_t* sig_u,
+                        const uint32_t* sig_R, const uint32_t* c, uint32_t* verdicts);
+/* the Hades tables the context derived from its parameters (rc 335, mds 25, pre 5, sparse 649, post 25 field
+ * elements, in that order, 1039 x 8 u32): compared with the Python twin of the derivation in the tests */
+int sb200_dbg_hades_tables(const sb200_ctx* ctx, uint32_t* out);
 
 #ifdef __cplusplus
 }

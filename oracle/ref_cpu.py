@@ -32,11 +32,15 @@ def _w(x):
     return [(x >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)]
 
 
+_rule = None
+
+
 def lib():
-    global _lib
-    if _lib is None:
+    global _lib, _rule
+    if _lib is None or _rule != o.ARK_RULE:  # (re)upload the constants: the oracle's round-constant rule may have changed
         build()
-        L = ctypes.CDLL(SO)
+        L = _lib or ctypes.CDLL(SO)
+        _rule = o.ARK_RULE
         blob = []
         blob += _w(o.Q) + _w(o.R)
         blob += [(-pow(o.Q, -1, 1 << 64)) % (1 << 64), (-pow(o.R, -1, 1 << 64)) % (1 << 64)]

@@ -20,7 +20,14 @@ the reference's own call sites (cited per function).  What pins it:
   * the reference's behavioural tests (sign->verify true, wrong key false, bytes round-trip,
     projective equality) re-run against this oracle (tests/test_reference_semantics.py).
 Nothing pins the Poseidon round constants / sponge padding numerically; the fingerprints in
-SURVEY.md §8(c) pin *this restatement* so drift is detected.
+SURVEY.md §8(c) pin *this restatement* (under the "plain" rule below) so drift is detected.
+
+ROUND-CONSTANT RULE.  dusk-hades' `ark.bin` is recalled in two forms (SURVEY.md §8(c) recall-risk item 1, VERDICT
+round 1): "cumsum" (`p = 1; c_i = from_bytes_wide(h_i) + p; p = c_i`, the recipe of assets/HOWTO.md as recalled
+by three independent reviews -- the default here and in the library) and "plain" (`c_i = from_bytes_wide(h_i)`,
+what round 1 shipped).  `set_ark_rule()` / the environment variable SB200_ARK switch the whole oracle;
+tests/golden/ holds one fixture set per rule, and rust/tests/dump_golden.rs regenerates the same JSON from the real
+crate, which is what finally settles it.
 
 Everything here is affine, big-int, slow and deliberately naive: scalar multiplication is the
 reference's 252-step MSB-first double-and-add, nothing is windowed, nothing is batched.
@@ -196,17 +203,38 @@ PARTIAL_ROUNDS = 59
 N_CONSTANTS = 960
 
 
-def _round_constants() -> List[int]:
-    """dusk-hades `ark.bin`: b = "poseidon-for-plonk"; repeat b = SHA-512(b);
-    constant = BlsScalar::from_bytes_wide(b)."""
-    out, b = [], b"poseidon-for-plonk"
+ARK_RULES = ("cumsum", "plain")
+
+
+def _round_constants(rule: str) -> List[int]:
+    """dusk-hades `ark.bin` (assets/HOWTO.md): b = "poseidon-for-plonk"; repeat b = SHA-512(b);
+    h = BlsScalar::from_bytes_wide(b);  "plain": constant = h;  "cumsum": constant = h + p, p = constant
+    (running sum seeded with p = 1)."""
+    assert rule in ARK_RULES, rule
+    out, b, p = [], b"poseidon-for-plonk", 1
     for _ in range(N_CONSTANTS):
         b = hashlib.sha512(b).digest()
-        out.append(int.from_bytes(b, "little") % Q)
+        c = int.from_bytes(b, "little") % Q
+        if rule == "cumsum":
+            c = (c + p) % Q
+            p = c
+        out.append(c)
     return out
 
 
-ROUND_CONSTANTS = _round_constants()
+import os as _os  # noqa: E402
+
+ARK_RULE = _os.environ.get("SB200_ARK") or "cumsum"
+ROUND_CONSTANTS = _round_constants(ARK_RULE)
+
+
+def set_ark_rule(rule: str) -> str:
+    """Switch the round-constant rule of the whole oracle (in place: every holder of ROUND_CONSTANTS sees it).
+    Returns the previous rule.  oracle/ref_cpu.py re-uploads its constant blob when the rule changed."""
+    global ARK_RULE
+    prev, ARK_RULE = ARK_RULE, rule
+    ROUND_CONSTANTS[:] = _round_constants(rule)
+    return prev
 # dusk-hades `mds.bin`: Cauchy matrix 1/(x_i + y_j), x_i = i, y_j = WIDTH + j.
 MDS = [[fq_inv(i + j + WIDTH) for j in range(WIDTH)] for i in range(WIDTH)]
 

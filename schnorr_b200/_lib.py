@@ -17,7 +17,50 @@ LIB_PATH = os.environ.get("SB200_LIB", os.path.join(_HERE, "libschnorr_b200.so")
 POINTS_PROJECTIVE = 0
 POINTS_AFFINE = 1
 DEVICE_PTRS = 2
-VERIFY_DUAL_PIPE = 4  # sb200_verify: warp-specialised kernel (hash warps on the FP64 pipe beside curve warps)
+VERIFY_DUAL_PIPE = 4  # sb200_verify, SB_EXPERIMENTAL_FD builds only: warp-specialised kernel (hash warps on the FP64 pipe)
+CHECK_POINTS = 8      # verify*: on-curve / Z != 0 check of every input point on the device
+ARK_CUMSUM, ARK_PLAIN, ARK_ENV = 0, 1, -1  # rules for the DEFAULT Hades round constants (include/schnorr_b200.h)
+ERR_ARG, ERR_CUDA, ERR_NODEV, ERR_NOMEM, ERR_PARAMS, ERR_BUSY = -1, -2, -3, -4, -5, -6
+
+
+class Params(ctypes.Structure):
+    """`sb200_params`: the two generators, the 335 Hades round constants and the MDS matrix, all as Montgomery limbs
+    (= dusk_bls12_381::BlsScalar's internal words).  Inputs of context creation, not baked constants."""
+    _fields_ = [("struct_size", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
+                ("generator", ctypes.c_uint32 * 16), ("generator_nums", ctypes.c_uint32 * 16),
+                ("round_constants", (ctypes.c_uint32 * 8) * 335), ("mds", ((ctypes.c_uint32 * 8) * 5) * 5)]
+
+    def view(self, field: str) -> np.ndarray:
+        """writable uint32 view of one field ([..., 8] limbs)"""
+        a = np.ctypeslib.as_array(getattr(self, field))
+        return a.reshape(-1, 8)
+
+
+def default_params(ark: int = ARK_ENV) -> Params:
+    """sb200_default_params: recalled generators, recipe-derived round constants (rule `ark`), Cauchy MDS."""
+    lib = load_library()
+    p = Params()
+    rc = lib.sb200_default_params(ark, ctypes.byref(p))
+    if rc != 0:
+        raise SchnorrB200Error(f"sb200_default_params: {lib.sb200_strerror(rc).decode()}")
+    return p
+
+
+def _split_tables(out: np.ndarray) -> dict:
+    cut = np.cumsum([0, 335, 25, 5, 649, 25])
+    return {k: out[cut[i]:cut[i + 1]].copy() for i, k in enumerate(("rc", "mds", "pre", "sparse", "post"))}
+
+
+def params_check(p: Params):
+    """sb200_params_check (host only): (return code, derived Hades tables or None)"""
+    lib = load_library()
+    out = aligned_empty((1039, 8))
+    rc = lib.sb200_params_check(ctypes.byref(p), out.ctypes.data)
+    return rc, (_split_tables(out) if rc == 0 else None)
+
+
+def ark_rule(name: Optional[str]) -> int:
+    return {None: ARK_ENV, "env": ARK_ENV, "cumsum": ARK_CUMSUM, "plain": ARK_PLAIN}[name]
 
 _lib = None
 
@@ -39,6 +82,13 @@ def load_library() -> ctypes.CDLL:
     vp, u32p, i64, u32, ci = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32, ctypes.c_int
     sig = {
         "sb200_init": (ci, [ctypes.POINTER(ci), ci, ctypes.POINTER(vp)]),
+        "sb200_init_ex": (ci, [vp, ctypes.POINTER(ci), ci, ctypes.POINTER(vp)]),
+        "sb200_default_params": (ci, [ci, vp]),
+        "sb200_get_params": (ci, [vp, vp]),
+        "sb200_params_check": (ci, [vp, u32p]),
+        "sb200_points_check": (ci, [vp, i64, u32] + [u32p] * 2),
+        "sb200_dbg_verify_ec": (ci, [vp, i64, u32] + [u32p] * 5),
+        "sb200_dbg_hades_tables": (ci, [vp, u32p]),
         "sb200_destroy": (None, [vp]),
         "sb200_strerror": (ctypes.c_char_p, [ci]),
         "sb200_last_error": (ctypes.c_char_p, [vp]),
@@ -62,10 +112,10 @@ def load_library() -> ctypes.CDLL:
         "sb200_fq_to_mont": (ci, [vp, i64, u32] + [u32p] * 2),
         "sb200_fq_from_mont": (ci, [vp, i64, u32] + [u32p] * 2),
         "sb200_verify_bytes": (ci, [vp, i64, u32] + [u32p] * 5),
-        "sb200_sign_bytes": (ci, [vp, i64, u32] + [u32p] * 4),
+        "sb200_sign_bytes": (ci, [vp, i64, u32] + [u32p] * 5),
         "sb200_verify_double_bytes": (ci, [vp, i64, u32] + [u32p] * 5),
         "sb200_verify_vargen_bytes": (ci, [vp, i64, u32] + [u32p] * 5),
-        "sb200_sign_double_bytes": (ci, [vp, i64, u32] + [u32p] * 4),
+        "sb200_sign_double_bytes": (ci, [vp, i64, u32] + [u32p] * 5),
         "sb200_sign_vargen_bytes": (ci, [vp, i64, u32] + [u32p] * 5),
         "sb200_dbg_fq": (ci, [vp, i64, ci] + [u32p] * 3),
         "sb200_dbg_fr_mul": (ci, [vp, i64] + [u32p] * 3),
@@ -80,6 +130,8 @@ def load_library() -> ctypes.CDLL:
 
 
 EXPORTED_SYMBOLS = [
+    "sb200_init_ex", "sb200_default_params", "sb200_get_params", "sb200_params_check", "sb200_points_check", "sb200_dbg_verify_ec",
+    "sb200_dbg_hades_tables",
     "sb200_init", "sb200_destroy", "sb200_strerror", "sb200_last_error", "sb200_device_count", "sb200_set_stream",
     "sb200_launch_count", "sb200_host_alloc", "sb200_host_free", "sb200_verify", "sb200_verify_double",
     "sb200_verify_vargen", "sb200_sign", "sb200_sign_double", "sb200_sign_vargen", "sb200_keygen",
@@ -95,6 +147,34 @@ def aligned_empty(shape, dtype=np.uint32, align=64) -> np.ndarray:
     raw = np.empty(n + align, dtype=np.uint8)
     off = (-raw.ctypes.data) % align
     return raw[off:off + n].view(dtype).reshape(shape)
+
+
+class PinnedBuffer:
+    """page-locked host memory from sb200_host_alloc, exposed as a numpy array (`.array`); freed on close() / GC"""
+
+    def __init__(self, shape, dtype=np.uint32):
+        lib = load_library()
+        self._lib = lib
+        nbytes = max(int(np.prod(shape)) * np.dtype(dtype).itemsize, 1)
+        p = ctypes.c_void_p()
+        rc = lib.sb200_host_alloc(nbytes, ctypes.byref(p))
+        if rc != 0:
+            raise SchnorrB200Error(f"sb200_host_alloc: {lib.sb200_strerror(rc).decode()}")
+        self._p = p
+        buf = (ctypes.c_uint8 * nbytes).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self.array = None
+            self._lib.sb200_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _arr(a, words: Optional[int], n: int, name: str) -> np.ndarray:
@@ -113,14 +193,19 @@ def _arr(a, words: Optional[int], n: int, name: str) -> np.ndarray:
 class Engine:
     """One sb200 context: comb tables for G and G' resident on each device, two streams per device."""
 
-    def __init__(self, devices: Optional[Sequence[int]] = None):
+    def __init__(self, devices: Optional[Sequence[int]] = None, params: Optional[Params] = None, ark: Optional[str] = None):
+        """`params`: an explicit sb200_params (e.g. the real crate's tables); else the defaults under round-constant
+        rule `ark` ("cumsum" | "plain" | None = environment variable SB200_ARK, default cumsum)."""
         self._lib = load_library()
         devs = list(devices) if devices is not None else [0]
         arr = (ctypes.c_int * len(devs))(*devs)
         h = ctypes.c_void_p()
-        rc = self._lib.sb200_init(arr, len(devs), ctypes.byref(h))
+        self.params = params if params is not None else default_params(ark_rule(ark))
+        rc = self._lib.sb200_init_ex(ctypes.byref(self.params), arr, len(devs), ctypes.byref(h))
         if rc != 0:
-            raise SchnorrB200Error(f"sb200_init failed: {self._lib.sb200_strerror(rc).decode()} (no CPU fallback)")
+            err = SchnorrB200Error(f"sb200_init_ex failed: {self._lib.sb200_strerror(rc).decode()} (no CPU fallback)")
+            err.code = rc
+            raise err
         self._h = h
         self.devices = devs
 
@@ -161,9 +246,9 @@ class Engine:
     def _unpack_bits(bitmap: np.ndarray, n: int) -> np.ndarray:
         return np.unpackbits(bitmap.view(np.uint8), bitorder="little")[:n].astype(bool)
 
-    def verify(self, pk, u, R, msg, affine=True, want_c=True, dual_pipe=False):
+    def verify(self, pk, u, R, msg, affine=True, want_c=True, dual_pipe=False, check_points=False):
         n = np.asarray(u).size // 8
-        pw, fl = self._pw(affine), (POINTS_AFFINE if affine else POINTS_PROJECTIVE) | (VERIFY_DUAL_PIPE if dual_pipe else 0)
+        pw, fl = self._pw(affine), (POINTS_AFFINE if affine else POINTS_PROJECTIVE) | (VERIFY_DUAL_PIPE if dual_pipe else 0) | (CHECK_POINTS if check_points else 0)
         pk, u, R, msg = _arr(pk, pw, n, "pk"), _arr(u, 8, n, "u"), _arr(R, pw, n, "R"), _arr(msg, 8, n, "msg")
         bm = aligned_empty(((n + 31) // 32,)); bm[...] = 0
         c = aligned_empty((n, 8)) if want_c else None
@@ -171,9 +256,9 @@ class Engine:
                   c.ctypes.data if want_c else None)
         return self._unpack_bits(bm, n), c
 
-    def verify_double(self, pk, pkp, u, R, Rp, msg, affine=True, want_c=True):
+    def verify_double(self, pk, pkp, u, R, Rp, msg, affine=True, want_c=True, check_points=False):
         n = np.asarray(u).size // 8
-        pw, fl = self._pw(affine), POINTS_AFFINE if affine else POINTS_PROJECTIVE
+        pw, fl = self._pw(affine), (POINTS_AFFINE if affine else POINTS_PROJECTIVE) | (CHECK_POINTS if check_points else 0)
         pk, pkp, R, Rp = _arr(pk, pw, n, "pk"), _arr(pkp, pw, n, "pk'"), _arr(R, pw, n, "R"), _arr(Rp, pw, n, "R'")
         u, msg = _arr(u, 8, n, "u"), _arr(msg, 8, n, "msg")
         bm = aligned_empty(((n + 31) // 32,)); bm[...] = 0
@@ -182,9 +267,9 @@ class Engine:
                   msg.ctypes.data, bm.ctypes.data, c.ctypes.data if want_c else None)
         return self._unpack_bits(bm, n), c
 
-    def verify_vargen(self, pk, gen, u, R, msg, affine=True, want_c=True):
+    def verify_vargen(self, pk, gen, u, R, msg, affine=True, want_c=True, check_points=False):
         n = np.asarray(u).size // 8
-        pw, fl = self._pw(affine), POINTS_AFFINE if affine else POINTS_PROJECTIVE
+        pw, fl = self._pw(affine), (POINTS_AFFINE if affine else POINTS_PROJECTIVE) | (CHECK_POINTS if check_points else 0)
         pk, gen, R = _arr(pk, pw, n, "pk"), _arr(gen, pw, n, "gen"), _arr(R, pw, n, "R")
         u, msg = _arr(u, 8, n, "u"), _arr(msg, 8, n, "msg")
         bm = aligned_empty(((n + 31) // 32,)); bm[...] = 0
@@ -296,12 +381,14 @@ class Engine:
         self.call("verify_bytes", n, 0, pk.ctypes.data, sig.ctypes.data, msg.ctypes.data, bm.ctypes.data, inv.ctypes.data)
         return self._unpack_bits(bm, n), self._unpack_bits(inv, n)
 
-    def sign_bytes(self, sk, msg, nonce):
+    def sign_bytes(self, sk, msg, nonce, want_invalid=False):
+        """sk, msg, nonce n x 32 -> sig n x 64 [, invalid[n]: a from_bytes of the tuple fails; its signature is all zero]"""
         sk, msg, nonce = self._bytes_arr(sk, 32, "sk"), self._bytes_arr(msg, 32, "msg"), self._bytes_arr(nonce, 32, "nonce")
         n = sk.shape[0]
         out = aligned_empty((n, 64), dtype=np.uint8)
-        self.call("sign_bytes", n, 0, sk.ctypes.data, msg.ctypes.data, nonce.ctypes.data, out.ctypes.data)
-        return out
+        inv = aligned_empty(((n + 31) // 32,)); inv[...] = 0
+        self.call("sign_bytes", n, 0, sk.ctypes.data, msg.ctypes.data, nonce.ctypes.data, out.ctypes.data, inv.ctypes.data)
+        return (out, self._unpack_bits(inv, n)) if want_invalid else out
 
     def _verify_bytes_generic(self, name, pk, pkw, sig, sigw, msg):
         pk, sig, msg = self._bytes_arr(pk, pkw, "pk"), self._bytes_arr(sig, sigw, "sig"), self._bytes_arr(msg, 32, "msg")
@@ -319,23 +406,47 @@ class Engine:
         """pk n x 64 (pk || generator), sig n x 64 (u || R), msg n x 32 -> (verdict[n], invalid[n])"""
         return self._verify_bytes_generic("verify_vargen_bytes", pk, 64, sig, 64, msg)
 
-    def sign_double_bytes(self, sk, msg, nonce):
+    def sign_double_bytes(self, sk, msg, nonce, want_invalid=False):
         sk, msg, nonce = self._bytes_arr(sk, 32, "sk"), self._bytes_arr(msg, 32, "msg"), self._bytes_arr(nonce, 32, "nonce")
         n = sk.shape[0]
         out = aligned_empty((n, 96), dtype=np.uint8)
-        self.call("sign_double_bytes", n, 0, sk.ctypes.data, msg.ctypes.data, nonce.ctypes.data, out.ctypes.data)
-        return out
+        inv = aligned_empty(((n + 31) // 32,)); inv[...] = 0
+        self.call("sign_double_bytes", n, 0, sk.ctypes.data, msg.ctypes.data, nonce.ctypes.data, out.ctypes.data, inv.ctypes.data)
+        return (out, self._unpack_bits(inv, n)) if want_invalid else out
 
     def sign_vargen_bytes(self, sk, msg, nonce):
-        """sk n x 64 (sk || generator) -> (sig n x 64, generator_ok[n])"""
+        """sk n x 64 (sk || generator) -> (sig n x 64, ok[n]: every from_bytes of the tuple succeeds)"""
         sk, msg, nonce = self._bytes_arr(sk, 64, "sk"), self._bytes_arr(msg, 32, "msg"), self._bytes_arr(nonce, 32, "nonce")
         n = sk.shape[0]
         out = aligned_empty((n, 64), dtype=np.uint8)
         bm = aligned_empty(((n + 31) // 32,)); bm[...] = 0
         self.call("sign_vargen_bytes", n, 0, sk.ctypes.data, msg.ctypes.data, nonce.ctypes.data, out.ctypes.data, bm.ctypes.data)
-        return out, self._unpack_bits(bm, n)
+        return out, ~self._unpack_bits(bm, n)
+
+    def points_check(self, points, affine=True):
+        """ok[n]: point i is on the curve with Z != 0 (what CHECK_POINTS applies inside the verify calls)"""
+        n = np.asarray(points).size // self._pw(affine)
+        p = _arr(points, self._pw(affine), n, "points")
+        bm = aligned_empty(((n + 31) // 32,)); bm[...] = 0
+        self.call("points_check", n, POINTS_AFFINE if affine else POINTS_PROJECTIVE, p.ctypes.data, bm.ctypes.data)
+        return self._unpack_bits(bm, n)
 
     # ---- building-block probes --------------------------------------------------------------------
+    def dbg_verify_ec(self, pk, u, R, c, affine=True):
+        """curve half of verify with caller-supplied challenges: verdict[i] = (u G + c PK == R)"""
+        n = np.asarray(u).size // 8
+        pw, fl = self._pw(affine), POINTS_AFFINE if affine else POINTS_PROJECTIVE
+        pk, u, R, c = _arr(pk, pw, n, "pk"), _arr(u, 8, n, "u"), _arr(R, pw, n, "R"), _arr(c, 8, n, "c")
+        bm = aligned_empty(((n + 31) // 32,)); bm[...] = 0
+        self.call("dbg_verify_ec", n, fl, pk.ctypes.data, u.ctypes.data, R.ctypes.data, c.ctypes.data, bm.ctypes.data)
+        return self._unpack_bits(bm, n)
+
+    def dbg_hades_tables(self):
+        """the Hades tables derived from this context's parameters: dict of [k, 8] Montgomery limb arrays"""
+        out = aligned_empty((1039, 8))
+        self._check(self._lib.sb200_dbg_hades_tables(self._h, out.ctypes.data), "dbg_hades_tables")
+        return _split_tables(out)
+
     def dbg_fq(self, op: int, a, b=None):
         n = np.asarray(a).size // 8
         a = _arr(a, 8, n, "a")

@@ -11,8 +11,15 @@
 #pragma once
 #include "ed.cuh"
 #include "hades.cuh"
-#include "hades_fd.cuh"
 #include "hgcd.cuh"
+// The FP64-pipe permutation is a measured experiment that lost; it is compiled only with
+// -DSB_EXPERIMENTAL_FD=1 (its tables are baked by tools/gen_constants.py, not context parameters).
+#ifndef SB_EXPERIMENTAL_FD
+#define SB_EXPERIMENTAL_FD 0
+#endif
+#if SB_EXPERIMENTAL_FD
+#include "experimental/hades_fd.cuh"
+#endif
 
 namespace sb200 {
 
@@ -21,6 +28,9 @@ namespace sb200 {
 // (the win comes from dedicating warps to it: k_verify_ws in schnorr_b200.cu).
 #ifndef SB_HADES_FD
 #define SB_HADES_FD 0
+#endif
+#if SB_HADES_FD && !SB_EXPERIMENTAL_FD
+#error "SB_HADES_FD needs SB_EXPERIMENTAL_FD"
 #endif
 SB_HD void chal3(const fq& Ru, const fq& Rv, const fq& m, uint32_t* c) {
 #if SB_HADES_FD
@@ -54,6 +64,17 @@ SB_HD void point_to_affine(const point_in& p, fq& u, fq& v) {
     u = fq_mul(p.U, zi);
     v = fq_mul(p.V, zi);
   }
+}
+
+// well-formed input point: on the curve and Z != 0 (SB200_CHECK_POINTS, sb200_points_check).  The reference's
+// constructors only produce such points; `from_raw_unchecked` (/root/reference/src/keys/public.rs:142,256,427) can
+// supply anything.   -U^2 Z^2 + V^2 Z^2 == Z^4 + d U^2 V^2   (Z = 1 when affine)
+SB_HD bool point_well_formed(const point_in& p) {
+  fq u2 = fq_sqr(p.U), v2 = fq_sqr(p.V);
+  fq lhs = fq_sub(v2, u2), duv = fq_mul(ed_d(), fq_mul(u2, v2));
+  if (p.affine) return fq_eq(lhs, fq_add(fq_one(), duv));
+  fq z2 = fq_sqr(p.Z);
+  return fq_eq(fq_mul(lhs, z2), fq_add(fq_sqr(z2), duv)) & !fq_is_zero(p.Z);
 }
 
 // completed point == R (projective equality u1*z2 == u2*z1 && v1*z2 == v2*z1, /root/reference/tests/keys.rs:52-58);
@@ -183,12 +204,14 @@ SB_HD void verify_hash_core(const point_in& R, const fq& m, uint32_t* c_out) {
   point_to_affine(R, ru, rv);
   chal3(ru, rv, m, c_out);
 }
+#if SB_EXPERIMENTAL_FD
 // ... on the FP64 pipe, permutation state in caller-provided slot storage (hades_fd.cuh)
 SB_HD void verify_hash_core_fd(const point_in& R, const fq& m, uint32_t* c_out, double* slots, int ls) {
   fq ru, rv;
   point_to_affine(R, ru, rv);
   challenge3_fd_p(ru, rv, m, c_out, slots, ls);
 }
+#endif
 
 SB_HD bool verify_core(const point_in& PK, const uint32_t* u_in, const point_in& R, const fq& m, const uint32_t* combG,
                        uint32_t* c_out) {

@@ -19,7 +19,8 @@
 //     fd_mul: a b / 2^260 + q;  2^260 / q ~ 35.3 leaves the head-room.
 // Host build: the same code with the DFMA pair emulated by a 128-bit product (tests/host_arith.cpp).
 #pragma once
-#include "fq.cuh"
+#include "../fq.cuh"
+#include "constants_fd_gen.cuh"
 
 #if defined(__CUDACC__)
 #define SB_HDC __host__ __device__ constexpr

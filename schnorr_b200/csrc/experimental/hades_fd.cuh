@@ -10,7 +10,7 @@
 // so the only stand-alone additions are the first round's keys and the sponge's second absorb.
 #pragma once
 #include "fd.cuh"
-#include "hades.cuh"
+#include "../hades.cuh"
 
 namespace sb200 {
 

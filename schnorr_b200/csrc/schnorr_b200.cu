@@ -16,8 +16,12 @@
 #include <string>
 #include <vector>
 
+#include <map>
+#include <thread>
+
 #include "../../include/schnorr_b200.h"
 #include "wire.cuh"
+#include "params_host.cuh"
 
 using namespace sb200;
 
@@ -25,7 +29,10 @@ namespace {
 
 constexpr int TPB = 128;
 #ifndef SB_CHALLENGE_FD
-#define SB_CHALLENGE_FD 0  // the stand-alone challenge kernel on the FP64 pipe instead of IMAD.WIDE: measured equal (182.94 vs 182.91 ms per 2^22 verifications)
+#define SB_CHALLENGE_FD 0  // the stand-alone challenge kernel on the FP64 pipe instead of IMAD.WIDE: measured equal (182.94 vs 182.91 ms per 2^22 verifications); needs SB_EXPERIMENTAL_FD
+#endif
+#if SB_CHALLENGE_FD && !SB_EXPERIMENTAL_FD
+#error "SB_CHALLENGE_FD needs SB_EXPERIMENTAL_FD"
 #endif
 #ifndef SB_MIN_CTAS
 #define SB_MIN_CTAS 4
@@ -37,14 +44,16 @@ constexpr int TPB = 128;
 #endif
 constexpr int min_ctas(int op) { return (op == 0 || op == 19) ? SB_VERIFY_CTAS : (op == 25 || op == 27) ? SB_MIN_CTAS - 1 : (op == 1 || op == 2) ? SB_MIN_CTAS - 1 : SB_MIN_CTAS; }
 constexpr int MAX_IN = 6, MAX_OUT = 4;
-constexpr int64_t CHUNK = 1 << 18;  // tuples per pipeline stage
+constexpr int64_t CHUNK = 1 << 18;      // tuples per pipeline stage ...
+constexpr int64_t CHUNK_MIN = 1 << 14;  // ... shrunk towards this when a device's share is under 4 chunks, so that H2D still overlaps compute
 
 enum Op : int {
   OP_VERIFY = 0, OP_VERIFY_DOUBLE, OP_VERIFY_VARGEN, OP_SIGN, OP_SIGN_DOUBLE, OP_SIGN_VARGEN,
   OP_KEYGEN, OP_KEYGEN_DOUBLE, OP_KEYGEN_VARGEN, OP_DBG_FQ, OP_DBG_FR_MUL, OP_DBG_HADES, OP_DBG_SMUL,
   OP_DECOMPRESS, OP_COMPRESS, OP_FROM_WIDE, OP_VERIFY_BYTES, OP_SIGN_BYTES, OP_CHALLENGE, OP_VERIFY_EC,
   OP_VERIFY_DOUBLE_BYTES, OP_VERIFY_VARGEN_BYTES, OP_SIGN_DOUBLE_BYTES, OP_SIGN_VARGEN_BYTES,
-  OP_CHALLENGE_DOUBLE, OP_VERIFY_DOUBLE_EC, OP_CHALLENGE_VARGEN, OP_VERIFY_VARGEN_EC
+  OP_CHALLENGE_DOUBLE, OP_VERIFY_DOUBLE_EC, OP_CHALLENGE_VARGEN, OP_VERIFY_VARGEN_EC, OP_POINTS_CHECK, OP_DBG_VERIFY_EC,
+  OP_DECODE_VERIFY
 };
 
 struct KArgs {
@@ -59,6 +68,9 @@ struct KArgs {
   struct WsState* ws;
   int nsm;
   pniels* ec_scratch;  // window tables of k_verify_ec_p: EC_P_CTAS * nsm * TPB threads x 18 entries (per stream)
+  uint8_t* scratch;          // device-only rows between the kernels of one call (challenges, decoded byte-level inputs)
+  const uint32_t* inv_mask;  // curve kernels: verdict word &= ~inv_mask word (tuples whose from_bytes failed)
+  uint32_t* dec[MAX_IN];     // decode kernel: where the decoded arrays of the byte-level verify calls go
 };
 
 // scheduling state of one warp-specialised launch (k_verify_ws): the next-tile counter, reset before every launch,
@@ -150,6 +162,25 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
     ldg_scalar(a.in[1] + i * 8, u);
     ldg_scalar(a.out[0] + i * 8, c);
     bool ok = verify_ec(ldg_point(a.in[0], i, aff), u, ldg_point(a.in[2], i, aff), c, a.combG);
+    if (a.flags & SB200_CHECK_POINTS) {  // warp-uniform
+#pragma unroll 1
+      for (int k = 0; k < 3; k += 2) ok &= point_well_formed(ldg_point(a.in[k], i, aff));
+    }
+    unsigned word = __ballot_sync(0xffffffffu, ok && active);
+    if ((threadIdx.x & 31) == 0 && active) a.bitmap[i >> 5] = a.inv_mask ? word & ~a.inv_mask[i >> 5] : word;
+    return;
+  }
+  if (OP == OP_DBG_VERIFY_EC) {  // in: pk, u, R, c -> bitmap
+    uint32_t u[8];
+    ldg_scalar(a.in[1] + i * 8, u);
+    ldg_scalar(a.in[3] + i * 8, c);
+    bool ok = verify_ec(ldg_point(a.in[0], i, aff), u, ldg_point(a.in[2], i, aff), c, a.combG);
+    unsigned word = __ballot_sync(0xffffffffu, ok && active);
+    if ((threadIdx.x & 31) == 0 && active) a.bitmap[i >> 5] = word;
+    return;
+  }
+  if (OP == OP_POINTS_CHECK) {  // in: points -> bitmap
+    bool ok = point_well_formed(ldg_point(a.in[0], i, aff));
     unsigned word = __ballot_sync(0xffffffffu, ok && active);
     if ((threadIdx.x & 31) == 0 && active) a.bitmap[i >> 5] = word;
     return;
@@ -165,8 +196,13 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
     ldg_scalar(a.in[2] + i * 8, u);
     ldg_scalar(a.out[0] + i * 8, c);
     bool ok = verify_vargen_ec(ldg_point(a.in[0], i, aff), ldg_point(a.in[1], i, aff), u, ldg_point(a.in[3], i, aff), c);
+    if (a.flags & SB200_CHECK_POINTS) {
+#pragma unroll 1
+      for (int k = 0; k < 4; k++)
+        if (k != 2) ok &= point_well_formed(ldg_point(a.in[k], i, aff));
+    }
     unsigned word = __ballot_sync(0xffffffffu, ok && active);
-    if ((threadIdx.x & 31) == 0 && active) a.bitmap[i >> 5] = word;
+    if ((threadIdx.x & 31) == 0 && active) a.bitmap[i >> 5] = a.inv_mask ? word & ~a.inv_mask[i >> 5] : word;
     return;
   }
   if (OP == OP_CHALLENGE_DOUBLE) {  // in: -, -, -, R, R', m -> out0: c
@@ -180,8 +216,49 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
     ldg_scalar(a.out[0] + i * 8, c);
     bool ok = verify_double_ec(ldg_point(a.in[0], i, aff), ldg_point(a.in[1], i, aff), u, ldg_point(a.in[3], i, aff),
                                ldg_point(a.in[4], i, aff), c, a.combG, a.combGp);
+    if (a.flags & SB200_CHECK_POINTS) {
+#pragma unroll 1
+      for (int k = 0; k < 5; k++)
+        if (k != 2) ok &= point_well_formed(ldg_point(a.in[k], i, aff));
+    }
     unsigned word = __ballot_sync(0xffffffffu, ok && active);
-    if ((threadIdx.x & 31) == 0 && active) a.bitmap[i >> 5] = word;
+    if ((threadIdx.x & 31) == 0 && active) a.bitmap[i >> 5] = a.inv_mask ? word & ~a.inv_mask[i >> 5] : word;
+    return;
+  }
+
+  // First kernel of the byte-level verify calls (sb200_verify{,_double,_vargen}_bytes): every from_bytes of the tuple
+  // -- JubJubAffine::from_bytes for the points (/root/reference/src/keys/public.rs:94-100, signatures.rs:119-122),
+  // JubJubScalar::from_bytes for u, BlsScalar::from_bytes for the message -- writing the decoded arrays in the layout
+  // the challenge and curve kernels read (affine Montgomery points, canonical u, Montgomery m) and the invalid bitmap.
+  // Its own launch: decompression (one 255-bit exponentiation per point) is a different code phase from the
+  // permutation and the curve loop, and the three do not fit the instruction cache together.
+  // aux: 0 single (pk32, sig64 -> pk, u, R, m), 1 double (pk64, sig96 -> pk, pk', u, R, R', m),
+  //      2 vargen (pk64, sig64 -> pk, gen, u, R, m).  in: pk bytes, sig bytes, msg32.
+  if (OP == OP_DECODE_VERIFY) {
+    const int npk = a.aux == 0 ? 1 : 2, nr = a.aux == 1 ? 2 : 1;
+    bool ok = true;
+#pragma unroll 1
+    for (int k = 0; k < npk + nr; k++) {  // one copy of the decompression code
+      const uint32_t* src = k < npk ? a.in[0] + i * (8 * npk) + 8 * k : a.in[1] + i * (8 + 8 * nr) + 8 + 8 * (k - npk);
+      uint32_t* dst = k < npk ? a.dec[k] : a.dec[npk + 1 + (k - npk)];
+      uint32_t b[8];
+      fq u, v;
+      ldg_scalar(src, b);
+      ok &= point_decompress(b, u, v);
+      if (active) stg_point(dst, i, u, v);
+    }
+    uint32_t us[8], mb[8];
+    fq m;
+    ldg_scalar(a.in[1] + i * (8 + 8 * nr), us);
+    ldg_scalar(a.in[2] + i * 8, mb);
+    ok &= scalar_lt_r(us);
+    ok &= msg_from_bytes(mb, m);
+    if (active) {
+      stg8(a.dec[npk] + i * 8, us);
+      stg8(a.dec[npk + 1 + nr] + i * 8, m.v);
+    }
+    unsigned inv = __ballot_sync(0xffffffffu, !ok && active);
+    if ((threadIdx.x & 31) == 0 && active) a.bitmap[i >> 5] = inv;
     return;
   }
 
@@ -253,6 +330,7 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
     fq s[5];
 #pragma unroll
     for (int k = 0; k < 5; k++) s[k] = ldg_fq(a.in[0] + i * 40 + k * 8);
+#if SB_EXPERIMENTAL_FD
     if (a.aux == 2) {  // FP64-pipe permutation (hades_fd.cuh); same Montgomery-2^256 words in and out
       fd t[5];
 #pragma unroll 1
@@ -263,7 +341,9 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
         fd_to_canonical(t[k], s[k].v);
         s[k] = fq_to_mont(s[k]);
       }
-    } else if (a.aux) hades_perm_dense(s); else hades_perm(s);
+    } else
+#endif
+    if (a.aux) hades_perm_dense(s); else hades_perm(s);
     if (active) {
 #pragma unroll
       for (int k = 0; k < 5; k++) stg8(a.out[0] + i * 40 + k * 8, s[k].v);
@@ -312,78 +392,29 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
     if (active) stg8(a.out[0] + i * 8, r);
     return;
   }
-  if (OP == OP_VERIFY_BYTES) {  // in: pk32, sig64, msg32 -> bitmap: verdicts, out0 (as bitmap): invalid
-    uint32_t pk[8], sig[16], m[8];
-    ldg_scalar(a.in[0] + i * 8, pk);
-    ldg_scalar(a.in[1] + i * 16, sig);
-    ldg_scalar(a.in[1] + i * 16 + 8, sig + 8);
-    ldg_scalar(a.in[2] + i * 8, m);
-    bool invalid;
-    bool ok = verify_bytes_core(pk, sig, m, a.combG, invalid);
-    unsigned word = __ballot_sync(0xffffffffu, ok && active), inv = __ballot_sync(0xffffffffu, invalid && active);
-    if ((threadIdx.x & 31) == 0 && active) {
-      a.bitmap[i >> 5] = word;
-      if (a.out[0]) a.out[0][i >> 5] = inv;
-    }
-    return;
-  }
-  if (OP == OP_VERIFY_DOUBLE_BYTES || OP == OP_VERIFY_VARGEN_BYTES) {  // in: pk64, sig96|sig64, msg32 -> bitmap, out0: invalid
-    constexpr int SW = OP == OP_VERIFY_DOUBLE_BYTES ? 24 : 16;
-    uint32_t pk[16], sig[SW], m[8];
-#pragma unroll
-    for (int k = 0; k < 2; k++) ldg_scalar(a.in[0] + i * 16 + 8 * k, pk + 8 * k);
-#pragma unroll
-    for (int k = 0; k < SW / 8; k++) ldg_scalar(a.in[1] + i * SW + 8 * k, sig + 8 * k);
-    ldg_scalar(a.in[2] + i * 8, m);
-    bool invalid, ok;
-    if (OP == OP_VERIFY_DOUBLE_BYTES) ok = verify_double_bytes_core(pk, sig, m, a.combG, a.combGp, invalid);
-    else ok = verify_vargen_bytes_core(pk, sig, m, invalid);
-    unsigned word = __ballot_sync(0xffffffffu, ok && active), inv = __ballot_sync(0xffffffffu, invalid && active);
-    if ((threadIdx.x & 31) == 0 && active) {
-      a.bitmap[i >> 5] = word;
-      if (a.out[0]) a.out[0][i >> 5] = inv;
-    }
-    return;
-  }
-  if (OP == OP_SIGN_DOUBLE_BYTES) {  // in: sk32, msg32, nonce32 -> out0: sig96 = u || R || R'
+  if (OP == OP_SIGN_DOUBLE_BYTES) {  // in: sk32, msg32, nonce32 -> out0: sig96 = u || R || R', bitmap (nullable): invalid
     uint32_t sk[8], nonce[8], mb[8], sig[24];
     ldg_scalar(a.in[0] + i * 8, sk);
     ldg_scalar(a.in[1] + i * 8, mb);
     ldg_scalar(a.in[2] + i * 8, nonce);
-    sign_double_bytes_core(sk, mb, nonce, a.combG, a.combGp, sig);
+    bool ok = sign_double_bytes_core(sk, mb, nonce, a.combG, a.combGp, sig);
+    unsigned inv = __ballot_sync(0xffffffffu, !ok && active);
+    if ((threadIdx.x & 31) == 0 && active && a.bitmap) a.bitmap[i >> 5] = inv;
     if (active) {
 #pragma unroll
       for (int k = 0; k < 3; k++) stg8(a.out[0] + i * 24 + 8 * k, sig + 8 * k);
     }
     return;
   }
-  if (OP == OP_SIGN_VARGEN_BYTES) {  // in: sk64 (sk || generator), msg32, nonce32 -> out0: sig64, bitmap: generator decoded
+  if (OP == OP_SIGN_VARGEN_BYTES) {  // in: sk64 (sk || generator), msg32, nonce32 -> out0: sig64, bitmap (nullable): invalid
     uint32_t sk[16], nonce[8], mb[8], sig[16];
     ldg_scalar(a.in[0] + i * 16, sk);
     ldg_scalar(a.in[0] + i * 16 + 8, sk + 8);
     ldg_scalar(a.in[1] + i * 8, mb);
     ldg_scalar(a.in[2] + i * 8, nonce);
     bool ok = sign_vargen_bytes_core(sk, mb, nonce, sig);
-    unsigned word = __ballot_sync(0xffffffffu, ok && active);
-    if ((threadIdx.x & 31) == 0 && active && a.bitmap) a.bitmap[i >> 5] = word;
-    if (active) {
-      stg8(a.out[0] + i * 16, sig);
-      stg8(a.out[0] + i * 16 + 8, sig + 8);
-    }
-    return;
-  }
-  if (OP == OP_SIGN_BYTES) {  // in: sk32, msg32 (canonical), nonce32 -> out0: sig64 = u || compress(R)
-    uint32_t sk[8], nonce[8], mb[8], u[8], sig[16];
-    fq Ru, Rv, mc;
-    ldg_scalar(a.in[0] + i * 8, sk);
-    ldg_scalar(a.in[1] + i * 8, mb);
-    ldg_scalar(a.in[2] + i * 8, nonce);
-#pragma unroll
-    for (int k = 0; k < 8; k++) mc.v[k] = mb[k];
-    sign_core(sk, nonce, fq_to_mont(mc), a.combG, u, Ru, Rv, c);
-#pragma unroll
-    for (int k = 0; k < 8; k++) sig[k] = u[k];
-    point_compress(Ru, Rv, sig + 8);
+    unsigned inv = __ballot_sync(0xffffffffu, !ok && active);
+    if ((threadIdx.x & 31) == 0 && active && a.bitmap) a.bitmap[i >> 5] = inv;
     if (active) {
       stg8(a.out[0] + i * 16, sig);
       stg8(a.out[0] + i * 16 + 8, sig + 8);
@@ -407,7 +438,7 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
 // straddle warps.
 // ------------------------------------------------------------------------------------------------
 #ifndef SB_VERIFY_WS
-#define SB_VERIFY_WS 1
+#define SB_VERIFY_WS SB_EXPERIMENTAL_FD  // compiled out of the product library: measured 22 % slower than the default path
 #endif
 #ifndef SB_VARGEN_SPLIT
 #define SB_VARGEN_SPLIT 1
@@ -424,6 +455,7 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
 #ifndef SB_WS_EREGS
 #define SB_WS_EREGS 120
 #endif
+#if SB_VERIFY_WS
 constexpr int WS_HW = 8, WS_EW = 8, WS_THREADS = (WS_HW + WS_EW) * 32, WS_EPER = 1;
 constexpr int WS_TILE = WS_EW * 32 * WS_EPER;       // 256 tuples per iteration
 constexpr int WS_HPER = WS_TILE / (WS_HW * 32);     // 1 hash per hash lane
@@ -495,11 +527,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_verify_ws(const KArgs a) {
   }
 }
 
+#endif  // SB_VERIFY_WS
+
 // Curve half of the single-key verification as a persistent kernel whose window tables live in a thread-major global
 // scratch region (18 entries x 128 B per resident thread) instead of local memory: see verify_ec_half.
 #ifndef SB_EC_GLOBAL_TABLES
 #define SB_EC_GLOBAL_TABLES 0  // measured: DRAM traffic 188 -> 32 GB per 2^22 launch, but the curve kernel takes 149 ms instead of 125 (L1 serves local memory write-back, global stores go through to L2): 20.4 vs 23.0 M verifies/s
 #endif
+#if SB_EC_GLOBAL_TABLES
 constexpr int EC_P_CTAS = 4;
 __global__ void __launch_bounds__(TPB, EC_P_CTAS) k_verify_ec_p(const KArgs a, pniels* scratch) {
   const bool aff = (a.flags & SB200_POINTS_AFFINE) != 0;
@@ -518,6 +553,8 @@ __global__ void __launch_bounds__(TPB, EC_P_CTAS) k_verify_ec_p(const KArgs a, p
     if ((threadIdx.x & 31) == 0 && active) a.bitmap[i >> 5] = word;
   }
 }
+
+#endif  // SB_EC_GLOBAL_TABLES
 
 // Fixed-base signing / key generation with several tuples per thread: the scalar multiples of G (and G') are
 // computed first, all their Z coordinates are inverted together (one field inversion per thread instead of one
@@ -548,6 +585,11 @@ __global__ void __launch_bounds__(TPB, 4) k_fixed_batch(const KArgs a) {
     if (i >= a.n) i = a.n - 1;
     uint32_t k[8];
     ldg_scalar(kin + i * 8, k);
+    if (OP == OP_SIGN_BYTES) {  // JubJubScalar::from_bytes of the nonce: >= r is reported invalid below, 0 keeps the recoding in range
+      const bool lt = scalar_lt_r(k);
+#pragma unroll
+      for (int w = 0; w < 8; w++) k[w] = lt ? k[w] : 0u;
+    }
     ext p = fixed_base_mul(a.combG, k);
     X[j] = p.X; Y[j] = p.Y; Z[j] = p.Z;
     if (DOUBLE) {
@@ -576,14 +618,29 @@ __global__ void __launch_bounds__(TPB, 4) k_fixed_batch(const KArgs a) {
     uint32_t sk[8], nonce[8], u[8], c[8];
     ldg_scalar(a.in[0] + i * 8, sk);
     ldg_scalar(a.in[2] + i * 8, nonce);
-    fq m = ldg_fq(a.in[1] + i * 8);
-    if (OP == OP_SIGN_BYTES) m = fq_to_mont(m);
+    fq m;
+    bool valid = true;
+    if (OP == OP_SIGN_BYTES) {  // the three from_bytes of the tuple; an invalid tuple gets an all-zero signature and its bit set
+      uint32_t mb[8], skb[8], nb[8];
+      ldg_scalar(a.in[1] + i * 8, mb);
+#pragma unroll
+      for (int w = 0; w < 8; w++) { skb[w] = sk[w]; nb[w] = nonce[w]; }
+      valid = sign_inputs_from_bytes(skb, nb, mb, sk, nonce, m);
+    } else {
+      m = ldg_fq(a.in[1] + i * 8);
+    }
     if (DOUBLE) chal5(Ru, Rv, Rpu, Rpv, m, c); else chal3(Ru, Rv, m, c);
     sign_finish(nonce, c, sk, u);
+    if (OP == OP_SIGN_BYTES) {
+      const unsigned inv = __ballot_sync(0xffffffffu, !valid && active);
+      if ((threadIdx.x & 31) == 0 && active && a.bitmap) a.bitmap[i >> 5] = inv;
+    }
     if (!active) continue;
     if (OP == OP_SIGN_BYTES) {
       uint32_t rb[8];
       point_compress(Ru, Rv, rb);
+#pragma unroll
+      for (int w = 0; w < 8; w++) { u[w] = valid ? u[w] : 0u; rb[w] = valid ? rb[w] : 0u; }
       stg8(a.out[0] + i * 16, u);
       stg8(a.out[0] + i * 16 + 8, rb);
     } else {
@@ -595,27 +652,42 @@ __global__ void __launch_bounds__(TPB, 4) k_fixed_batch(const KArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(TPB) k_comb_build(uint32_t* table, int which) {
+__global__ void __launch_bounds__(TPB) k_comb_build(uint32_t* table, const fq bu, const fq bv) {
   int t = blockIdx.x * TPB + threadIdx.x;
   if (t >= COMB_WINDOWS * COMB_ENTRIES) return;  // 524 304 entries at 16-bit windows
-  const fq gu = {SB200_G_U_INIT}, gv = {SB200_G_V_INIT}, hu = {SB200_GP_U_INIT}, hv = {SB200_GP_V_INIT};
-  comb_build_entry(which ? hu : gu, which ? hv : gv, t / COMB_ENTRIES, t % COMB_ENTRIES, table + (size_t)t * 24);
+  comb_build_entry(bu, bv, t / COMB_ENTRIES, t % COMB_ENTRIES, table + (size_t)t * 24);
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+struct Stage {  // pinned staging buffer for pageable host memory
+  uint8_t* p = nullptr;
+  size_t cap = 0;
+};
+struct PendingCopy {  // results sitting in a pinned out-stage until their D2H has landed
+  uint8_t* dst;
+  const uint8_t* src;
+  size_t bytes;
+};
 struct DevCtx {
   int dev = 0;
   cudaStream_t stream[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};  // end of the work enqueued for a pipeline slot
   uint32_t* combG = nullptr;
   uint32_t* combGp = nullptr;
   uint8_t* arena[2] = {nullptr, nullptr};
   size_t arena_cap[2] = {0, 0};
+  Stage hin[2], hout[2];
+  std::vector<PendingCopy> pending[2];
   WsState* ws[3] = {nullptr, nullptr, nullptr};  // per pipeline stream, [2] = caller's stream (SB200_DEVICE_PTRS)
-  pniels* ec_scratch[3] = {nullptr, nullptr, nullptr};  // k_verify_ec_p window tables, per stream like ws
-  uint32_t* cscratch = nullptr;                  // challenges of a SB200_DEVICE_PTRS verify call without c_out
+  pniels* ec_scratch[3] = {nullptr, nullptr, nullptr};  // k_verify_ec_p window tables (SB_EC_GLOBAL_TABLES builds only)
+  uint32_t* cscratch = nullptr;                  // device-only rows of a SB200_DEVICE_PTRS call (scratch_bytes)
   size_t cscratch_cap = 0;
+  cudaEvent_t user_ev = nullptr;                 // last SB200_DEVICE_PTRS work of this context (orders a stream switch)
+  cudaStream_t last_user_stream = nullptr;
+  bool user_ev_valid = false;
+  bool registered = false;                       // holds a reference on this device's constant-memory parameters
   int nsm = 0;
 };
 
@@ -631,14 +703,41 @@ struct Desc {
   uint32_t* bitmap = nullptr;
 };
 
+// Hades tables live in each device's constant memory: one parameter set per process and device.
+struct DevParams {
+  uint64_t hash = 0;
+  int refs = 0;
+};
+std::mutex g_params_mu;
+std::map<int, DevParams> g_dev_params;
+
+uint64_t fnv1a(const void* p, size_t n) {
+  const uint8_t* b = (const uint8_t*)p;
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
+  return h;
+}
+
+struct DeviceGuard {  // the caller's current device is restored when a call returns
+  int prev = -1;
+  DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 }  // namespace
 
 struct sb200_ctx {
   std::vector<DevCtx> devs;
-  std::mutex mu;
+  std::mutex mu, err_mu;
   std::string err;
   cudaStream_t user_stream = nullptr;
   std::atomic<uint64_t> launches{0};
+  sb200_params params;
+  HadesTables tables;
+  void set_err(const std::string& e) {
+    std::lock_guard<std::mutex> l(err_mu);
+    if (err.empty() || e.empty()) err = e;
+  }
 };
 
 namespace {
@@ -647,7 +746,7 @@ namespace {
   do {                                                                                        \
     cudaError_t _e = (call);                                                                  \
     if (_e != cudaSuccess) {                                                                  \
-      ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e);                          \
+      ctx->set_err(std::string(#call) + ": " + cudaGetErrorString(_e));                       \
       return SB200_ERR_CUDA;                                                                  \
     }                                                                                         \
   } while (0)
@@ -667,6 +766,39 @@ int launch(sb200_ctx* ctx, Op op, const KArgs& a, cudaStream_t st) {
     return SB200_OK;
   }
 #endif
+  if (op == OP_VERIFY_BYTES || op == OP_VERIFY_DOUBLE_BYTES || op == OP_VERIFY_VARGEN_BYTES) {
+    // decode kernel -> challenge kernel -> curve kernel, the decoded rows and the challenges in a.scratch
+    const int scheme = op == OP_VERIFY_BYTES ? 0 : op == OP_VERIFY_DOUBLE_BYTES ? 1 : 2;
+    const int npk = scheme == 0 ? 1 : 2, nr = scheme == 1 ? 2 : 1, narr = npk + 1 + nr + 1;
+    uint8_t* p = a.scratch;
+    auto carve = [&](size_t bytes) { uint8_t* r = p; p += (bytes + 63) & ~(size_t)63; return (uint32_t*)r; };
+    KArgs dk = a, v = a;
+    dk.aux = scheme;
+    v.flags = (a.flags & SB200_DEVICE_PTRS) | SB200_POINTS_AFFINE;
+    v.out[0] = carve((size_t)a.n * 32);
+    for (int k = 0; k < narr; k++) {
+      const bool is_scalar = (k == npk) || (k == narr - 1);  // u and m are 8 words, points 16
+      dk.dec[k] = carve((size_t)a.n * (is_scalar ? 32 : 64));
+      v.in[k] = dk.dec[k];
+    }
+    dk.bitmap = a.out[0] ? a.out[0] : carve((size_t)((a.n + 31) / 32) * 4);  // the caller's `invalid` or scratch
+    v.inv_mask = dk.bitmap;
+    for (int k = 1; k < MAX_OUT; k++) v.out[k] = nullptr;
+    k_run<OP_DECODE_VERIFY><<<grid, TPB, 0, st>>>(dk);
+    if (scheme == 0) {
+      k_run<OP_CHALLENGE><<<grid, TPB, 0, st>>>(v);
+      k_run<OP_VERIFY_EC><<<grid, TPB, 0, st>>>(v);
+    } else if (scheme == 1) {
+      k_run<OP_CHALLENGE_DOUBLE><<<grid, TPB, 0, st>>>(v);
+      k_run<OP_VERIFY_DOUBLE_EC><<<grid, TPB, 0, st>>>(v);
+    } else {
+      k_run<OP_CHALLENGE_VARGEN><<<grid, TPB, 0, st>>>(v);
+      k_run<OP_VERIFY_VARGEN_EC><<<grid, TPB, 0, st>>>(v);
+    }
+    ctx->launches.fetch_add(3, std::memory_order_relaxed);
+    CU(cudaGetLastError());
+    return SB200_OK;
+  }
 #if SB_VERIFY_SPLIT
   if (op == OP_VERIFY) {  // a.out[0] is always set here: the caller's c_out or scratch
     k_run<OP_CHALLENGE><<<grid, TPB, 0, st>>>(a);
@@ -703,179 +835,421 @@ int launch(sb200_ctx* ctx, Op op, const KArgs& a, cudaStream_t st) {
 #define CASE(O) case O: k_run<O><<<grid, TPB, 0, st>>>(a); break;
     CASE(OP_VERIFY) CASE(OP_VERIFY_DOUBLE) CASE(OP_VERIFY_VARGEN) CASE(OP_SIGN_VARGEN)
     CASE(OP_KEYGEN_VARGEN) CASE(OP_DBG_FQ) CASE(OP_DBG_FR_MUL) CASE(OP_DBG_HADES)
-    CASE(OP_DBG_SMUL) CASE(OP_DECOMPRESS) CASE(OP_COMPRESS) CASE(OP_FROM_WIDE) CASE(OP_VERIFY_BYTES)
-    CASE(OP_VERIFY_DOUBLE_BYTES) CASE(OP_VERIFY_VARGEN_BYTES) CASE(OP_SIGN_DOUBLE_BYTES) CASE(OP_SIGN_VARGEN_BYTES)
+    CASE(OP_DBG_SMUL) CASE(OP_DECOMPRESS) CASE(OP_COMPRESS) CASE(OP_FROM_WIDE)
+    CASE(OP_SIGN_DOUBLE_BYTES) CASE(OP_SIGN_VARGEN_BYTES)
+    CASE(OP_POINTS_CHECK) CASE(OP_DBG_VERIFY_EC)
 #undef CASE
+    default: return SB200_ERR_ARG;
   }
   ctx->launches.fetch_add(1, std::memory_order_relaxed);
   CU(cudaGetLastError());
   return SB200_OK;
 }
 
+bool splits_with_scratch(const Desc& d) {  // hash and curve kernels hand c over in memory
+  return SB_VERIFY_SPLIT && ((d.op == OP_VERIFY && !(d.flags & SB200_VERIFY_DUAL_PIPE)) || d.op == OP_VERIFY_DOUBLE ||
+                             (SB_VARGEN_SPLIT && d.op == OP_VERIFY_VARGEN)) && !d.out[0];
+}
+
+// device-only bytes between the kernels of one call over n tuples: challenges (split verification without c_out),
+// plus the decoded rows and the invalid bitmap of the byte-level verify calls
+size_t scratch_bytes(const Desc& d, int64_t n) {
+  size_t per = 0;
+  int arrays = 0;
+  switch (d.op) {
+    case OP_VERIFY_BYTES: per = 32 + (16 + 8 + 16 + 8) * 4; arrays = 6; break;
+    case OP_VERIFY_DOUBLE_BYTES: per = 32 + (16 * 4 + 8 + 8) * 4; arrays = 8; break;
+    case OP_VERIFY_VARGEN_BYTES: per = 32 + (16 * 3 + 8 + 8) * 4; arrays = 7; break;
+    default: per = splits_with_scratch(d) ? 32 : 0; arrays = per ? 1 : 0; break;
+  }
+  if (!per) return 0;
+  return (size_t)n * per + (size_t)((n + 31) / 32) * 4 + 64 * (arrays + 1);
+}
+
+bool host_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+int grow_stage(sb200_ctx* ctx, Stage& s, size_t need) {
+  if (s.cap >= need) return SB200_OK;
+  if (s.p) cudaFreeHost(s.p);
+  s.p = nullptr; s.cap = 0;
+  if (cudaHostAlloc((void**)&s.p, need, cudaHostAllocPortable) != cudaSuccess) { ctx->set_err("cudaHostAlloc staging"); return SB200_ERR_NOMEM; }
+  s.cap = need;
+  return SB200_OK;
+}
+
+// wait for a pipeline slot's work and move its staged results to the caller's (pageable) buffers
+int drain_slot(sb200_ctx* ctx, DevCtx& dc, int slot) {
+  if (dc.pending[slot].empty()) return SB200_OK;
+  CU(cudaEventSynchronize(dc.done[slot]));
+  for (auto& c : dc.pending[slot]) memcpy(c.dst, c.src, c.bytes);
+  dc.pending[slot].clear();
+  return SB200_OK;
+}
+
+// One device's share [lo, hi) of a host-buffer call: chunks alternate between two streams (H2D / kernels / D2H of
+// consecutive chunks overlap); pageable host arrays go through the slot's pinned stage.
+int run_device(sb200_ctx* ctx, DevCtx& dc, const Desc& d, int64_t lo, int64_t hi, size_t per_tuple,
+               const bool* in_pinned, const bool* out_pinned, bool bm_pinned) {
+  CU(cudaSetDevice(dc.dev));
+  const int64_t share = hi - lo;
+  int64_t chunk = CHUNK;
+  if (share < 4 * CHUNK) chunk = std::max<int64_t>(CHUNK_MIN, (((share + 3) / 4) + 31) & ~(int64_t)31);
+  size_t in_stage = 0, out_stage = 0;  // staging bytes per tuple
+  for (int k = 0; k < d.nin; k++) if (d.in_words[k] && !in_pinned[k]) in_stage += (size_t)d.in_words[k] * 4;
+  for (int k = 0; k < d.nout; k++) if (d.out[k] && d.out_words[k] > 0 && !out_pinned[k]) out_stage += (size_t)d.out_words[k] * 4;
+  int slot = 0;
+  for (int64_t c0 = lo; c0 < hi; c0 += chunk, slot ^= 1) {
+    const int64_t cn = std::min<int64_t>(chunk, hi - c0);
+    const size_t bm_bytes = (size_t)((cn + 31) / 32) * 4;
+    int rc = drain_slot(ctx, dc, slot);  // also frees the slot's stages
+    if (rc) return rc;
+    if (in_stage) CU(cudaEventSynchronize(dc.done[slot]));  // the in-stage may still be read by the slot's previous H2D
+    const size_t scr = scratch_bytes(d, cn);
+    size_t need = (size_t)cn * per_tuple + scr + bm_bytes * (1 + MAX_OUT) + 64 * (MAX_IN + MAX_OUT + 2);
+    if (dc.arena_cap[slot] < need) {
+      CU(cudaStreamSynchronize(dc.stream[slot]));
+      if (dc.arena[slot]) CU(cudaFree(dc.arena[slot]));
+      dc.arena[slot] = nullptr; dc.arena_cap[slot] = 0;
+      const int64_t full = std::min<int64_t>(chunk, share);
+      size_t cap = std::max(need, (size_t)full * per_tuple + scratch_bytes(d, full) + (1 << 20));
+      if (cudaMalloc(&dc.arena[slot], cap) != cudaSuccess) { ctx->set_err("cudaMalloc arena"); return SB200_ERR_NOMEM; }
+      dc.arena_cap[slot] = cap;
+    }
+    if (in_stage && (rc = grow_stage(ctx, dc.hin[slot], (size_t)chunk * in_stage + 64 * MAX_IN))) return rc;
+    if ((out_stage || !bm_pinned) && (rc = grow_stage(ctx, dc.hout[slot], (size_t)chunk * out_stage + ((size_t)(chunk + 31) / 32 * 4 + 64) * (MAX_OUT + 1)))) return rc;
+    cudaStream_t st = dc.stream[slot];
+    uint8_t *p = dc.arena[slot], *hi_p = dc.hin[slot].p, *ho_p = dc.hout[slot].p;
+    auto carve = [](uint8_t*& q, size_t bytes) { uint8_t* r = q; q += (bytes + 63) & ~(size_t)63; return r; };
+    KArgs a{};
+    a.n = cn; a.flags = d.flags; a.aux = d.aux; a.combG = dc.combG; a.combGp = dc.combGp;
+    a.ws = dc.ws[slot]; a.nsm = dc.nsm; a.ec_scratch = dc.ec_scratch[slot];
+    for (int k = 0; k < d.nin; k++) {
+      if (!d.in_words[k]) continue;
+      size_t bytes = (size_t)cn * d.in_words[k] * 4;
+      uint32_t* dp = (uint32_t*)carve(p, bytes);
+      const uint8_t* src = (const uint8_t*)(d.in[k] + (size_t)c0 * d.in_words[k]);
+      if (!in_pinned[k]) {
+        uint8_t* sp = carve(hi_p, bytes);
+        memcpy(sp, src, bytes);
+        src = sp;
+      }
+      CU(cudaMemcpyAsync(dp, src, bytes, cudaMemcpyHostToDevice, st));
+      a.in[k] = dp;
+    }
+    uint32_t* dout[MAX_OUT] = {};
+    auto out_bytes = [&](int k) {  // out_words == -1: bitmap-shaped output (one word per 32 tuples)
+      return d.out_words[k] < 0 ? bm_bytes : (size_t)cn * d.out_words[k] * 4;
+    };
+    for (int k = 0; k < d.nout; k++)
+      if (d.out[k]) a.out[k] = dout[k] = (uint32_t*)carve(p, out_bytes(k));
+    if (scr) {
+      a.scratch = carve(p, scr);
+      if (splits_with_scratch(d)) a.out[0] = (uint32_t*)a.scratch;
+    }
+    uint32_t* dbm = nullptr;
+    if (d.bitmap) a.bitmap = dbm = (uint32_t*)carve(p, bm_bytes);
+    if ((rc = launch(ctx, d.op, a, st))) return rc;
+    auto d2h = [&](uint32_t* host_dst, const uint32_t* dev_src, size_t bytes, bool pinned) -> int {
+      uint8_t* dst = (uint8_t*)host_dst;
+      if (!pinned) {
+        uint8_t* sp = carve(ho_p, bytes);
+        dc.pending[slot].push_back({dst, sp, bytes});
+        dst = sp;
+      }
+      CU(cudaMemcpyAsync(dst, dev_src, bytes, cudaMemcpyDeviceToHost, st));
+      return SB200_OK;
+    };
+    for (int k = 0; k < d.nout; k++)
+      if (d.out[k] && (rc = d2h(d.out_words[k] < 0 ? d.out[k] + c0 / 32 : d.out[k] + (size_t)c0 * d.out_words[k], dout[k],
+                                out_bytes(k), d.out_words[k] < 0 ? bm_pinned : out_pinned[k])))
+        return rc;
+    if (d.bitmap && (rc = d2h(d.bitmap + c0 / 32, dbm, bm_bytes, bm_pinned))) return rc;
+    CU(cudaEventRecord(dc.done[slot], st));
+  }
+  for (int s = 0; s < 2; s++) {
+    int rc = drain_slot(ctx, dc, s);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(dc.stream[s]));
+  }
+  return SB200_OK;
+}
+
+// after a failure nothing may still be reading or writing the caller's buffers when the call returns
+void quiesce(DevCtx& dc) {
+  cudaSetDevice(dc.dev);
+  for (int s = 0; s < 2; s++) {
+    if (dc.stream[s]) cudaStreamSynchronize(dc.stream[s]);
+    dc.pending[s].clear();
+  }
+  cudaGetLastError();
+}
+
 int run(sb200_ctx* ctx, int64_t n, const Desc& d) {
   if (!ctx || n < 0) return SB200_ERR_ARG;
-  if (d.flags & ~(SB200_POINTS_AFFINE | SB200_DEVICE_PTRS | (d.op == OP_VERIFY ? SB200_VERIFY_DUAL_PIPE : 0u))) return SB200_ERR_ARG;
+  uint32_t allowed = SB200_POINTS_AFFINE | SB200_DEVICE_PTRS;
+  if (d.op == OP_VERIFY && SB_VERIFY_WS) allowed |= SB200_VERIFY_DUAL_PIPE;
+  if (d.op == OP_VERIFY || d.op == OP_VERIFY_DOUBLE || d.op == OP_VERIFY_VARGEN) allowed |= SB200_CHECK_POINTS;
+  if (d.flags & ~allowed) return SB200_ERR_ARG;
   for (int k = 0; k < d.nin; k++)
     if (d.in_words[k] && (!d.in[k] || ((uintptr_t)d.in[k] & 15))) return SB200_ERR_ARG;
   for (int k = 0; k < d.nout; k++)
     if (d.out[k] && ((uintptr_t)d.out[k] & 15)) return SB200_ERR_ARG;
   if (n == 0) return SB200_OK;
   std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->set_err("");
+  DeviceGuard guard;
 
   if (d.flags & SB200_DEVICE_PTRS) {
     if (ctx->devs.size() != 1) return SB200_ERR_ARG;
     DevCtx& dc = ctx->devs[0];
     CU(cudaSetDevice(dc.dev));
+    cudaStream_t st = ctx->user_stream;
+    // the scratch buffers below are shared by all SB200_DEVICE_PTRS calls of this context: order a stream switch
+    if (dc.user_ev_valid && dc.last_user_stream != st) CU(cudaStreamWaitEvent(st, dc.user_ev, 0));
     KArgs a{};
     a.n = n; a.flags = d.flags; a.aux = d.aux; a.combG = dc.combG; a.combGp = dc.combGp; a.bitmap = d.bitmap;
     a.ws = dc.ws[2]; a.nsm = dc.nsm; a.ec_scratch = dc.ec_scratch[2];
     for (int k = 0; k < d.nin; k++) a.in[k] = d.in[k];
     for (int k = 0; k < d.nout; k++) a.out[k] = d.out[k];
-#if SB_VERIFY_SPLIT
-    if (((d.op == OP_VERIFY && !(d.flags & SB200_VERIFY_DUAL_PIPE)) || d.op == OP_VERIFY_DOUBLE || (SB_VARGEN_SPLIT && d.op == OP_VERIFY_VARGEN)) && !a.out[0]) {  // hash and curve kernels hand c over in memory
-      size_t need = (size_t)n * 32;
-      if (dc.cscratch_cap < need) {
-        CU(cudaStreamSynchronize(ctx->user_stream));
+    if (const size_t need = scratch_bytes(d, n)) {
+      if (dc.cscratch_cap < need) {  // grows on first use / larger batches only (a cudaMalloc in the call path)
+        if (dc.user_ev_valid) CU(cudaEventSynchronize(dc.user_ev));
         if (dc.cscratch) CU(cudaFree(dc.cscratch));
         dc.cscratch = nullptr; dc.cscratch_cap = 0;
-        if (cudaMalloc(&dc.cscratch, need) != cudaSuccess) { ctx->err = "cudaMalloc challenge scratch"; return SB200_ERR_NOMEM; }
+        if (cudaMalloc(&dc.cscratch, need) != cudaSuccess) { ctx->set_err("cudaMalloc scratch"); return SB200_ERR_NOMEM; }
         dc.cscratch_cap = need;
       }
-      a.out[0] = dc.cscratch;
+      a.scratch = (uint8_t*)dc.cscratch;
+      if (splits_with_scratch(d)) a.out[0] = dc.cscratch;
     }
-#endif
-    return launch(ctx, d.op, a, ctx->user_stream);
+    int rc = launch(ctx, d.op, a, st);
+    if (rc) return rc;
+    CU(cudaEventRecord(dc.user_ev, st));
+    dc.user_ev_valid = true;
+    dc.last_user_stream = st;
+    return SB200_OK;
   }
 
   // bytes per tuple on the device arena (every array padded to 16 B; bitmap = 4 B per 32 tuples)
   size_t per_tuple = 0;
-  for (int k = 0; k < d.nin; k++) per_tuple += (size_t)d.in_words[k] * 4;
-  for (int k = 0; k < d.nout; k++) per_tuple += (d.out[k] && d.out_words[k] > 0) ? (size_t)d.out_words[k] * 4 : 0;
-  const bool c_scratch = SB_VERIFY_SPLIT && (d.op == OP_VERIFY || d.op == OP_VERIFY_DOUBLE || (SB_VARGEN_SPLIT && d.op == OP_VERIFY_VARGEN)) && !d.out[0];  // device-only challenge rows between the two kernels
-  if (c_scratch) per_tuple += 32;
+  bool in_pinned[MAX_IN] = {}, out_pinned[MAX_OUT] = {}, bm_pinned = true;
+  for (int k = 0; k < d.nin; k++) {
+    per_tuple += (size_t)d.in_words[k] * 4;
+    if (d.in_words[k]) in_pinned[k] = host_pinned(d.in[k]);
+  }
+  for (int k = 0; k < d.nout; k++) {
+    per_tuple += (d.out[k] && d.out_words[k] > 0) ? (size_t)d.out_words[k] * 4 : 0;
+    if (d.out[k]) out_pinned[k] = host_pinned(d.out[k]);
+    if (d.out[k] && d.out_words[k] < 0) bm_pinned = bm_pinned && out_pinned[k];
+  }
+  if (d.bitmap) bm_pinned = bm_pinned && host_pinned(d.bitmap);
 
   const int ndev = (int)ctx->devs.size();
-  int64_t per_dev = ((n + ndev - 1) / ndev + 31) & ~(int64_t)31;
-  for (int di = 0; di < ndev; di++) {
-    DevCtx& dc = ctx->devs[di];
-    int64_t lo = std::min<int64_t>(n, di * per_dev), hi = std::min<int64_t>(n, lo + per_dev);
-    if (lo >= hi) continue;
-    CU(cudaSetDevice(dc.dev));
-    int slot = 0;
-    for (int64_t c0 = lo; c0 < hi; c0 += CHUNK, slot ^= 1) {
-      int64_t cn = std::min<int64_t>(CHUNK, hi - c0);
-      size_t need = (size_t)cn * per_tuple + (size_t)((cn + 31) / 32) * 4 * (1 + MAX_OUT) + 64 * (MAX_IN + MAX_OUT + 1);
-      if (dc.arena_cap[slot] < need) {
-        CU(cudaStreamSynchronize(dc.stream[slot]));
-        if (dc.arena[slot]) CU(cudaFree(dc.arena[slot]));
-        dc.arena[slot] = nullptr; dc.arena_cap[slot] = 0;
-        size_t cap = std::max(need, (size_t)std::min<int64_t>(CHUNK, per_dev) * per_tuple + (1 << 20));
-        if (cudaMalloc(&dc.arena[slot], cap) != cudaSuccess) { ctx->err = "cudaMalloc arena"; return SB200_ERR_NOMEM; }
-        dc.arena_cap[slot] = cap;
-      }
-      cudaStream_t st = dc.stream[slot];
-      uint8_t* p = dc.arena[slot];
-      auto carve = [&](size_t bytes) { uint8_t* r = p; p += (bytes + 63) & ~(size_t)63; return r; };
-      KArgs a{};
-      a.n = cn; a.flags = d.flags; a.aux = d.aux; a.combG = dc.combG; a.combGp = dc.combGp;
-      a.ws = dc.ws[slot]; a.nsm = dc.nsm; a.ec_scratch = dc.ec_scratch[slot];
-      for (int k = 0; k < d.nin; k++) {
-        if (!d.in_words[k]) continue;
-        size_t bytes = (size_t)cn * d.in_words[k] * 4;
-        uint32_t* dp = (uint32_t*)carve(bytes);
-        CU(cudaMemcpyAsync(dp, d.in[k] + (size_t)c0 * d.in_words[k], bytes, cudaMemcpyHostToDevice, st));
-        a.in[k] = dp;
-      }
-      uint32_t* dout[MAX_OUT] = {};
-      auto out_bytes = [&](int k) {  // out_words == -1: bitmap-shaped output (one word per 32 tuples)
-        return d.out_words[k] < 0 ? (size_t)((cn + 31) / 32) * 4 : (size_t)cn * d.out_words[k] * 4;
-      };
-      for (int k = 0; k < d.nout; k++)
-        if (d.out[k]) a.out[k] = dout[k] = (uint32_t*)carve(out_bytes(k));
-      if (c_scratch) a.out[0] = (uint32_t*)carve((size_t)cn * 32);
-      uint32_t* dbm = nullptr;
-      if (d.bitmap) a.bitmap = dbm = (uint32_t*)carve((size_t)((cn + 31) / 32) * 4);
-      int rc = launch(ctx, d.op, a, st);
-      if (rc) return rc;
-      for (int k = 0; k < d.nout; k++)
-        if (d.out[k])
-          CU(cudaMemcpyAsync(d.out_words[k] < 0 ? d.out[k] + c0 / 32 : d.out[k] + (size_t)c0 * d.out_words[k], dout[k],
-                             out_bytes(k), cudaMemcpyDeviceToHost, st));
-      if (d.bitmap)
-        CU(cudaMemcpyAsync(d.bitmap + c0 / 32, dbm, (size_t)((cn + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
-    }
+  const int64_t per_dev = ((n + ndev - 1) / ndev + 31) & ~(int64_t)31;
+  std::vector<int> rcs(ndev, SB200_OK);
+  auto work = [&](int di) {
+    const int64_t lo = std::min<int64_t>(n, di * per_dev), hi = std::min<int64_t>(n, lo + per_dev);
+    if (lo < hi) rcs[di] = run_device(ctx, ctx->devs[di], d, lo, hi, per_tuple, in_pinned, out_pinned, bm_pinned);
+  };
+  if (ndev == 1) {
+    work(0);
+  } else {  // one host thread per device: staging copies and (for pageable memory, blocking) transfers run in parallel
+    std::vector<std::thread> th;
+    for (int di = 1; di < ndev; di++) th.emplace_back(work, di);
+    work(0);
+    for (auto& t : th) t.join();
   }
-  for (auto& dc : ctx->devs) {
-    CU(cudaSetDevice(dc.dev));
-    CU(cudaStreamSynchronize(dc.stream[0]));
-    CU(cudaStreamSynchronize(dc.stream[1]));
-  }
-  return SB200_OK;
+  int rc = SB200_OK;
+  for (int di = 0; di < ndev; di++)
+    if (rcs[di] && !rc) rc = rcs[di];
+  if (rc)
+    for (auto& dc : ctx->devs) quiesce(dc);
+  return rc;
 }
 
 int pt_words(uint32_t flags) { return (flags & SB200_POINTS_AFFINE) ? 16 : 24; }
+
+void release_device(DevCtx& dc) {
+  cudaSetDevice(dc.dev);
+  for (int s = 0; s < 2; s++) {
+    if (dc.stream[s]) { cudaStreamSynchronize(dc.stream[s]); cudaStreamDestroy(dc.stream[s]); }
+    if (dc.done[s]) cudaEventDestroy(dc.done[s]);
+    if (dc.arena[s]) cudaFree(dc.arena[s]);
+    if (dc.hin[s].p) cudaFreeHost(dc.hin[s].p);
+    if (dc.hout[s].p) cudaFreeHost(dc.hout[s].p);
+  }
+  if (dc.user_ev) { if (dc.user_ev_valid) cudaEventSynchronize(dc.user_ev); cudaEventDestroy(dc.user_ev); }
+  if (dc.combG) cudaFree(dc.combG);
+  if (dc.combGp) cudaFree(dc.combGp);
+  for (int s = 0; s < 3; s++) {
+    if (dc.ws[s]) cudaFree(dc.ws[s]);
+    if (dc.ec_scratch[s]) cudaFree(dc.ec_scratch[s]);
+  }
+  if (dc.cscratch) cudaFree(dc.cscratch);
+  if (dc.registered) {
+    std::lock_guard<std::mutex> l(g_params_mu);
+    auto it = g_dev_params.find(dc.dev);
+    if (it != g_dev_params.end() && --it->second.refs <= 0) g_dev_params.erase(it);
+  }
+  dc = DevCtx();
+}
+
+// parameters -> validated, derived, self-checked tables.  Host only.
+int prepare_params(const sb200_params* p, HadesTables& T) {
+  if (!p || p->struct_size != sizeof(sb200_params) || p->reserved != 0) return SB200_ERR_ARG;
+  const uint32_t* all = p->generator;
+  const size_t nfe = (sizeof(sb200_params) - 8) / 32;
+  for (size_t i = 0; i < nfe; i++)
+    if (!params::canonical_fq(all + 8 * i)) return SB200_ERR_PARAMS;
+  const fq gu = params::ld(p->generator), gv = params::ld(p->generator + 8);
+  const fq hu = params::ld(p->generator_nums), hv = params::ld(p->generator_nums + 8);
+  if (!params::on_curve(gu, gv) || !params::on_curve(hu, hv)) return SB200_ERR_PARAMS;
+  if (!params::prime_order(gu, gv) || !params::prime_order(hu, hv)) return SB200_ERR_PARAMS;
+  if (!params::derive_hades_tables(p->round_constants, p->mds, T)) return SB200_ERR_PARAMS;
+  // self-check: the sparse form must reproduce the reference-shaped dense permutation (host build of the same code)
+  h_hades = T;
+  uint64_t s = 0x9e3779b97f4a7c15ull;
+  for (int trial = 0; trial < 3; trial++) {
+    fq a[5], b[5];
+    for (int k = 0; k < 5; k++) {
+      for (int j = 0; j < 8; j++) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; a[k].v[j] = trial ? (uint32_t)s : 0u; }
+      a[k].v[7] &= 0x3fffffffu;
+      b[k] = a[k];
+    }
+    hades_perm_dense(a);
+    hades_perm(b);
+    for (int k = 0; k < 5; k++)
+      if (!fq_eq(a[k], b[k])) return SB200_ERR_PARAMS;
+  }
+  return SB200_OK;
+}
 
 }  // namespace
 
 extern "C" {
 
+int sb200_default_params(int ark_rule, sb200_params* out) {
+  if (!out) return SB200_ERR_ARG;
+  if (ark_rule == SB200_ARK_ENV) {
+    const char* e = getenv("SB200_ARK");
+    ark_rule = (e && !strcmp(e, "plain")) ? SB200_ARK_PLAIN : SB200_ARK_CUMSUM;
+    if (e && strcmp(e, "plain") && strcmp(e, "cumsum") && *e) return SB200_ERR_ARG;
+  }
+  if (ark_rule != SB200_ARK_CUMSUM && ark_rule != SB200_ARK_PLAIN) return SB200_ERR_ARG;
+  memset(out, 0, sizeof(*out));
+  out->struct_size = sizeof(sb200_params);
+  const uint32_t g[4][8] = {SB200_G_U_INIT, SB200_G_V_INIT, SB200_GP_U_INIT, SB200_GP_V_INIT};
+  memcpy(out->generator, g[0], 32); memcpy(out->generator + 8, g[1], 32);
+  memcpy(out->generator_nums, g[2], 32); memcpy(out->generator_nums + 8, g[3], 32);
+  params::default_round_constants(ark_rule, out->round_constants, 335);
+  params::default_mds(out->mds);
+  return SB200_OK;
+}
+
 int sb200_init(const int* devices, int n_devices, sb200_ctx** out) {
+  sb200_params p;
+  int rc = sb200_default_params(SB200_ARK_ENV, &p);
+  if (rc) return rc;
+  return sb200_init_ex(&p, devices, n_devices, out);
+}
+
+int sb200_init_ex(const sb200_params* params_in, const int* devices, int n_devices, sb200_ctx** out) {
   if (!out || n_devices < 0 || (n_devices > 0 && !devices)) return SB200_ERR_ARG;
   *out = nullptr;
-  int count = 0;
-  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return SB200_ERR_NODEV;
-  int dflt = 0;
-  if (n_devices == 0) { devices = &dflt; n_devices = 1; }
   sb200_ctx* ctx = new sb200_ctx();
   auto fail = [&](int code) { sb200_destroy(ctx); return code; };
+  int rc = prepare_params(params_in, ctx->tables);
+  if (rc) return fail(rc);
+  ctx->params = *params_in;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail(SB200_ERR_NODEV);
+  DeviceGuard guard;
+  int dflt = 0;
+  if (n_devices == 0) { devices = &dflt; n_devices = 1; }
+  const uint64_t hash = fnv1a(params_in, sizeof(*params_in));
+  const fq gu = params::ld(params_in->generator), gv = params::ld(params_in->generator + 8);
+  const fq hu = params::ld(params_in->generator_nums), hv = params::ld(params_in->generator_nums + 8);
+  ctx->devs.reserve(n_devices);
   for (int i = 0; i < n_devices; i++) {
     if (devices[i] < 0 || devices[i] >= count) return fail(SB200_ERR_ARG);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, devices[i]) != cudaSuccess || prop.major < 10) return fail(SB200_ERR_NODEV);
-    DevCtx dc;
+    ctx->devs.emplace_back();  // owned by the context from here on: sb200_destroy releases whatever got allocated
+    DevCtx& dc = ctx->devs.back();
     dc.dev = devices[i];
     if (cudaSetDevice(dc.dev) != cudaSuccess) return fail(SB200_ERR_CUDA);
-    for (int s = 0; s < 2; s++)
+    {  // this device's constant memory holds one parameter set
+      std::lock_guard<std::mutex> l(g_params_mu);
+      DevParams& dp = g_dev_params[dc.dev];
+      if (dp.refs > 0 && dp.hash != hash) return fail(SB200_ERR_BUSY);
+      if (dp.refs == 0 || dp.hash != hash) {
+        if (cudaMemcpyToSymbol(d_hades, &ctx->tables, sizeof(HadesTables)) != cudaSuccess) return fail(SB200_ERR_CUDA);
+        dp.hash = hash;
+      }
+      dp.refs++;
+      dc.registered = true;
+    }
+    for (int s = 0; s < 2; s++) {
       if (cudaStreamCreateWithFlags(&dc.stream[s], cudaStreamNonBlocking) != cudaSuccess) return fail(SB200_ERR_CUDA);
+      if (cudaEventCreateWithFlags(&dc.done[s], cudaEventDisableTiming) != cudaSuccess) return fail(SB200_ERR_CUDA);
+    }
+    if (cudaEventCreateWithFlags(&dc.user_ev, cudaEventDisableTiming) != cudaSuccess) return fail(SB200_ERR_CUDA);
     size_t tb = (size_t)COMB_WINDOWS * COMB_ENTRIES * 24 * 4;
     if (cudaMalloc(&dc.combG, tb) != cudaSuccess || cudaMalloc(&dc.combGp, tb) != cudaSuccess) return fail(SB200_ERR_NOMEM);
     dc.nsm = prop.multiProcessorCount;
+#if SB_VERIFY_WS
     if (cudaFuncSetAttribute(k_verify_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM) != cudaSuccess) return fail(SB200_ERR_CUDA);
     for (int s = 0; s < 3; s++)
       if (cudaMalloc(&dc.ws[s], sizeof(WsState)) != cudaSuccess || cudaMemset(dc.ws[s], 0, sizeof(WsState)) != cudaSuccess)
         return fail(SB200_ERR_NOMEM);
+#endif
 #if SB_EC_GLOBAL_TABLES
     for (int s = 0; s < 3; s++)  // 4 x 148 x 128 threads x 2 304 B = 175 MB per stream
       if (cudaMalloc(&dc.ec_scratch[s], (size_t)EC_P_CTAS * dc.nsm * TPB * 18 * sizeof(pniels)) != cudaSuccess) return fail(SB200_ERR_NOMEM);
 #endif
-    ctx->devs.push_back(dc);
     int grid = (COMB_WINDOWS * COMB_ENTRIES + TPB - 1) / TPB;
-    k_comb_build<<<grid, TPB, 0, dc.stream[0]>>>(dc.combG, 0);
-    k_comb_build<<<grid, TPB, 0, dc.stream[0]>>>(dc.combGp, 1);
+    k_comb_build<<<grid, TPB, 0, dc.stream[0]>>>(dc.combG, gu, gv);
+    k_comb_build<<<grid, TPB, 0, dc.stream[0]>>>(dc.combGp, hu, hv);
     ctx->launches += 2;
-    if (cudaStreamSynchronize(dc.stream[0]) != cudaSuccess) return fail(SB200_ERR_CUDA);
   }
+  for (auto& dc : ctx->devs)  // the table builds of all devices run concurrently
+    if (cudaSetDevice(dc.dev) != cudaSuccess || cudaStreamSynchronize(dc.stream[0]) != cudaSuccess) return fail(SB200_ERR_CUDA);
   *out = ctx;
   return SB200_OK;
 }
 
 void sb200_destroy(sb200_ctx* ctx) {
   if (!ctx) return;
-  for (auto& dc : ctx->devs) {
-    cudaSetDevice(dc.dev);
-    for (int s = 0; s < 2; s++) {
-      if (dc.stream[s]) { cudaStreamSynchronize(dc.stream[s]); cudaStreamDestroy(dc.stream[s]); }
-      if (dc.arena[s]) cudaFree(dc.arena[s]);
-    }
-    if (dc.combG) cudaFree(dc.combG);
-    if (dc.combGp) cudaFree(dc.combGp);
-    for (int s = 0; s < 3; s++)
-      if (dc.ws[s]) cudaFree(dc.ws[s]);
-    if (dc.cscratch) cudaFree(dc.cscratch);
-    for (int s = 0; s < 3; s++)
-      if (dc.ec_scratch[s]) cudaFree(dc.ec_scratch[s]);
+  {
+    DeviceGuard guard;
+    for (auto& dc : ctx->devs) release_device(dc);
   }
   delete ctx;
+}
+
+int sb200_params_check(const sb200_params* params_in, uint32_t* tables_out) {
+  HadesTables* T = new HadesTables();
+  int rc = prepare_params(params_in, *T);
+  if (!rc && tables_out) memcpy(tables_out, T, sizeof(HadesTables));
+  delete T;
+  return rc;
+}
+int sb200_get_params(const sb200_ctx* ctx, sb200_params* out) {
+  if (!ctx || !out) return SB200_ERR_ARG;
+  *out = ctx->params;
+  return SB200_OK;
+}
+int sb200_dbg_hades_tables(const sb200_ctx* ctx, uint32_t* out) {
+  if (!ctx || !out) return SB200_ERR_ARG;
+  memcpy(out, &ctx->tables, sizeof(HadesTables));
+  return SB200_OK;
 }
 
 const char* sb200_strerror(int code) {
@@ -885,10 +1259,12 @@ const char* sb200_strerror(int code) {
     case SB200_ERR_CUDA: return "CUDA error";
     case SB200_ERR_NODEV: return "no usable sm_100 CUDA device";
     case SB200_ERR_NOMEM: return "out of device memory";
+    case SB200_ERR_PARAMS: return "scheme parameters rejected";
+    case SB200_ERR_BUSY: return "device already holds different scheme parameters";
     default: return "unknown error";
   }
 }
-const char* sb200_last_error(const sb200_ctx* ctx) { return ctx ? ctx->err.c_str() : ""; }
+const char* sb200_last_error(const sb200_ctx* ctx) { return ctx ? ctx->err.c_str() : ""; }  // valid until the context's next call
 int sb200_device_count(const sb200_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
 int sb200_set_stream(sb200_ctx* ctx, void* s) {
   if (!ctx) return SB200_ERR_ARG;
@@ -1006,9 +1382,9 @@ int sb200_verify_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t*
   return run(ctx, n, d);
 }
 int sb200_sign_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* sk, const uint8_t* msg, const uint8_t* nonce,
-                     uint8_t* sig_out) {
+                     uint8_t* sig_out, uint32_t* invalid) {
   if (!sig_out || (flags & SB200_POINTS_AFFINE)) return SB200_ERR_ARG;
-  Desc d; d.op = OP_SIGN_BYTES; d.flags = flags; d.nin = 3; d.nout = 1;
+  Desc d; d.op = OP_SIGN_BYTES; d.flags = flags; d.nin = 3; d.nout = 1; d.bitmap = invalid;
   IN(0, (const uint32_t*)sk, 8); IN(1, (const uint32_t*)msg, 8); IN(2, (const uint32_t*)nonce, 8); OUT(0, (uint32_t*)sig_out, 16);
   return run(ctx, n, d);
 }
@@ -1029,17 +1405,30 @@ int sb200_verify_vargen_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const u
   return run(ctx, n, d);
 }
 int sb200_sign_double_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* sk, const uint8_t* msg, const uint8_t* nonce,
-                            uint8_t* sig_out) {
+                            uint8_t* sig_out, uint32_t* invalid) {
   if (!sig_out || (flags & SB200_POINTS_AFFINE)) return SB200_ERR_ARG;
-  Desc d; d.op = OP_SIGN_DOUBLE_BYTES; d.flags = flags; d.nin = 3; d.nout = 1;
+  Desc d; d.op = OP_SIGN_DOUBLE_BYTES; d.flags = flags; d.nin = 3; d.nout = 1; d.bitmap = invalid;
   IN(0, (const uint32_t*)sk, 8); IN(1, (const uint32_t*)msg, 8); IN(2, (const uint32_t*)nonce, 8); OUT(0, (uint32_t*)sig_out, 24);
   return run(ctx, n, d);
 }
 int sb200_sign_vargen_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* sk, const uint8_t* msg, const uint8_t* nonce,
-                            uint8_t* sig_out, uint32_t* ok_bitmap) {
-  if (!sig_out || !ok_bitmap || (flags & SB200_POINTS_AFFINE)) return SB200_ERR_ARG;
-  Desc d; d.op = OP_SIGN_VARGEN_BYTES; d.flags = flags | SB200_POINTS_AFFINE; d.nin = 3; d.nout = 1; d.bitmap = ok_bitmap;
+                            uint8_t* sig_out, uint32_t* invalid) {
+  if (!sig_out || (flags & SB200_POINTS_AFFINE)) return SB200_ERR_ARG;
+  Desc d; d.op = OP_SIGN_VARGEN_BYTES; d.flags = flags | SB200_POINTS_AFFINE; d.nin = 3; d.nout = 1; d.bitmap = invalid;
   IN(0, (const uint32_t*)sk, 16); IN(1, (const uint32_t*)msg, 8); IN(2, (const uint32_t*)nonce, 8); OUT(0, (uint32_t*)sig_out, 16);
+  return run(ctx, n, d);
+}
+int sb200_points_check(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* points, uint32_t* ok_bitmap) {
+  if (!ok_bitmap) return SB200_ERR_ARG;
+  Desc d; d.op = OP_POINTS_CHECK; d.flags = flags; d.nin = 1; d.nout = 0; d.bitmap = ok_bitmap;
+  IN(0, points, pt_words(flags));
+  return run(ctx, n, d);
+}
+int sb200_dbg_verify_ec(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* pk, const uint32_t* sig_u, const uint32_t* sig_R,
+                        const uint32_t* c, uint32_t* verdicts) {
+  if (!verdicts) return SB200_ERR_ARG;
+  Desc d; d.op = OP_DBG_VERIFY_EC; d.flags = flags; d.nin = 4; d.nout = 0; d.bitmap = verdicts;
+  IN(0, pk, pt_words(flags)); IN(1, sig_u, 8); IN(2, sig_R, pt_words(flags)); IN(3, c, 8);
   return run(ctx, n, d);
 }
 int sb200_dbg_fq(sb200_ctx* ctx, int64_t n, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
@@ -1055,7 +1444,7 @@ int sb200_dbg_fr_mul(sb200_ctx* ctx, int64_t n, const uint32_t* a, const uint32_
   return run(ctx, n, d);
 }
 int sb200_dbg_hades(sb200_ctx* ctx, int64_t n, int dense, uint32_t* states) {
-  if (!states) return SB200_ERR_ARG;
+  if (!states || dense < 0 || dense > (SB_EXPERIMENTAL_FD ? 2 : 1)) return SB200_ERR_ARG;
   Desc d; d.op = OP_DBG_HADES; d.flags = 0; d.aux = dense; d.nin = 1; d.nout = 1;
   IN(0, states, 40); OUT(0, states, 40);
   return run(ctx, n, d);

@@ -262,27 +262,58 @@ SB_HD bool verify_vargen_bytes_core(const uint32_t* pk64, const uint32_t* sig64,
   return ok & verdict;
 }
 
-// SecretKey::sign_double -> SignatureDouble::to_bytes (secret.rs:217-240, signatures.rs:245-258): sig96 = u || R || R'
-SB_HD void sign_double_bytes_core(const uint32_t* sk32, const uint32_t* msg32, const uint32_t* nonce32, const uint32_t* combG,
+// The from_bytes of a signing tuple: SecretKey::from_bytes / JubJubScalar::from_bytes (reject >= r,
+// /root/reference/src/keys/secret.rs:96-102) for sk and the nonce, BlsScalar::from_bytes (reject >= q) for the message.
+// Returns false where the reference would return Err(InvalidData); the values are then replaced by 0 so the
+// arithmetic below stays in range (a nonce >= 2^252 would overflow the window recoding), and the caller emits no
+// signature for that tuple.
+SB_HD bool sign_inputs_from_bytes(const uint32_t* sk32, const uint32_t* nonce32, const uint32_t* msg32, uint32_t* sk,
+                                  uint32_t* nonce, fq& m) {
+  uint32_t a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    a[i] = sk32[i];
+    b[i] = nonce32[i];
+  }
+  bool ok = scalar_lt_r(a) & scalar_lt_r(b);
+  ok &= msg_from_bytes(msg32, m);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    sk[i] = ok ? a[i] : 0u;
+    nonce[i] = ok ? b[i] : 0u;
+  }
+  if (!ok) m = fq_zero();
+  return ok;
+}
+
+// SecretKey::sign_double -> SignatureDouble::to_bytes (secret.rs:217-240, signatures.rs:245-258): sig96 = u || R || R'.
+// false <=> a from_bytes fails; sig96 is then all zero.
+SB_HD bool sign_double_bytes_core(const uint32_t* sk32, const uint32_t* msg32, const uint32_t* nonce32, const uint32_t* combG,
                                   const uint32_t* combGp, uint32_t* sig96) {
   fq m, Ru, Rv, Rpu, Rpv;
-  uint32_t c[8];
-  msg_from_bytes(msg32, m);
-  sign_double_core(sk32, nonce32, m, combG, combGp, sig96, Ru, Rv, Rpu, Rpv, c);
+  uint32_t c[8], sk[8], nonce[8];
+  bool ok = sign_inputs_from_bytes(sk32, nonce32, msg32, sk, nonce, m);
+  sign_double_core(sk, nonce, m, combG, combGp, sig96, Ru, Rv, Rpu, Rpv, c);
   point_compress(Ru, Rv, sig96 + 8);
   point_compress(Rpu, Rpv, sig96 + 16);
+#pragma unroll
+  for (int i = 0; i < 24; i++) sig96[i] = ok ? sig96[i] : 0u;
+  return ok;
 }
 
 // SecretKeyVarGen::from_bytes (sk || generator, secret.rs:313-336) + sign (secret.rs:433-451) +
-// SignatureVarGen::to_bytes: sig64 = u || R.  false <=> the generator does not decode.
+// SignatureVarGen::to_bytes: sig64 = u || R.  false <=> a from_bytes fails (sk, nonce, message, or the generator does
+// not decode); sig64 is then all zero.
 SB_HD bool sign_vargen_bytes_core(const uint32_t* sk64, const uint32_t* msg32, const uint32_t* nonce32, uint32_t* sig64) {
   point_in GEN;
   bool ok = point_from_bytes(sk64 + 8, GEN);
   fq m, Ru, Rv;
-  uint32_t c[8];
-  msg_from_bytes(msg32, m);
-  sign_vargen_core(sk64, GEN, nonce32, m, sig64, Ru, Rv, c);
+  uint32_t c[8], sk[8], nonce[8];
+  ok &= sign_inputs_from_bytes(sk64, nonce32, msg32, sk, nonce, m);
+  sign_vargen_core(sk, GEN, nonce, m, sig64, Ru, Rv, c);
   point_compress(Ru, Rv, sig64 + 8);
+#pragma unroll
+  for (int i = 0; i < 16; i++) sig64[i] = ok ? sig64[i] : 0u;
   return ok;
 }
 

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Regenerate tests/golden/schnorr_golden.json.
+"""Regenerate tests/golden/schnorr_golden_{cumsum,plain}.json (one fixture set per round-constant rule).
 
 PROVENANCE -- read before trusting these vectors.  The reference (dusk-schnorr 0.18, Rust) holds NO
 known-answer vectors and cannot be compiled in this image (no cargo/rustc; its arithmetic lives in
@@ -16,10 +16,19 @@ The "fingerprints" block is different: it is copied from SURVEY.md section 8(c),
 independent throw-away restatement in another session -- two independent restatements agreeing is the
 strongest pin available here ("parity unpinned" against the real crate).
 
-What the file pins: (1) the oracle against silent drift, (2) the CUDA path byte-for-byte at the wire level
+What the files pin: (1) the oracle against silent drift, (2) the CUDA path byte-for-byte at the wire level
 (`to_bytes()` forms), (3) the RNG stream (seed -> nonce) used for "same seeded stream" signing.
 
-Usage:  python tests/golden/make_golden.py        (rewrites schnorr_golden.json next to this file)
+TWO FILES, because dusk-hades' round-constant table is recalled in two forms (oracle/schnorr_oracle.py
+"ROUND-CONSTANT RULE"): `schnorr_golden_cumsum.json` (running sum seeded with one -- the default) and
+`schnorr_golden_plain.json` (round 1's rule; the SURVEY fingerprints belong to this one).  Everything that does not
+pass through Poseidon (keys, nonces, RNG known answers) is identical in both.
+
+THE SAME JSON FROM THE REAL CRATE: `rust/tests/dump_golden.rs` replays exactly this recipe through dusk-schnorr and
+writes `schnorr_golden_crate.json` in the same schema; tests/test_golden.py picks that file up unchanged when it is
+dropped next to the other two and reports which rule (if any) it agrees with.  That closes "parity unpinned".
+
+Usage:  python tests/golden/make_golden.py        (rewrites both files next to this script)
 """
 import json
 import os
@@ -73,9 +82,8 @@ def vargen_case(rng):
             "c": hx(c), "valid": True}
 
 
-def main():
-    out = {"about": "oracle-generated (NOT reference-generated) vectors; see make_golden.py",
-           "fingerprints": {  # SURVEY.md 8(c), computed independently of oracle/
+def survey_fingerprints():
+    return {  # SURVEY.md 8(c), computed independently of oracle/ ("plain" rule)
                "rc0": "4929e824cae3e5b6915af89c2b2ef56233518da79404494933a12bb7322dd246",
                "rc1": "16c704062c23752559d045399f2fc29ca7db44d857dc2a6a7385f58eba0d4801",
                "rc334": "069d59d29d2260b3510923ee9d8845734a67b558bafd4be62dcfc3cf34028be9",
@@ -90,7 +98,25 @@ def main():
                "stdrng_construction_seed": "0100000017000000c8010000d21e0000" + "00" * 16,
                "stdrng_construction_first_u64": 10719222850664546238,
                "stdrng_construction_from_rng_u64": 14064965282130556830,
-           }}
+    }
+
+
+def oracle_fingerprints():
+    """the same keys computed by the oracle under its current rule (NOT an independent source)"""
+    bh = lambda x: "%064x" % x
+    fp = survey_fingerprints()
+    fp.update({"rc0": bh(o.ROUND_CONSTANTS[0]), "rc1": bh(o.ROUND_CONSTANTS[1]), "rc334": bh(o.ROUND_CONSTANTS[334]),
+               "perm_zero_word1": bh(o.hades_perm([0] * 5)[1]),
+               "sponge_1_2_3": bh(o.sponge_hash([1, 2, 3])), "trunc_1_2_3": bh(o.truncated_hash([1, 2, 3])),
+               "sponge_1_2_3_4_5": bh(o.sponge_hash([1, 2, 3, 4, 5])), "trunc_1_2_3_4_5": bh(o.truncated_hash([1, 2, 3, 4, 5]))})
+    return fp
+
+
+def make(rule):
+    o.set_ark_rule(rule)
+    out = {"about": "oracle-generated (NOT reference-generated) vectors; see make_golden.py", "ark": rule,
+           "fingerprints_source": "SURVEY.md 8(c), independent restatement" if rule == "plain" else "oracle (not independent)",
+           "fingerprints": survey_fingerprints() if rule == "plain" else oracle_fingerprints()}
     # the reference's own recipes
     out["single"] = [single_case(o.StdRng.seed_from_u64(2321))]
     out["double"] = [double_case(o.StdRng.seed_from_u64(2321))]
@@ -132,11 +158,18 @@ def main():
         sR = o.affine_from_bytes(bytes.fromhex(e["sig"][64:]))
         e["valid"] = bool(o.verify(pk, su, sR, int.from_bytes(bytes.fromhex(e["msg"]), "little")))
     out["single_verify_cases"] = neg
-    path = os.path.join(HERE, "schnorr_golden.json")
+    path = os.path.join(HERE, "schnorr_golden_%s.json" % rule)
     with open(path, "w") as f:
         json.dump(out, f, indent=1)
         f.write("\n")
     print("wrote", path, {k: len(v) for k, v in out.items() if isinstance(v, list)})
+
+
+def main():
+    prev = o.ARK_RULE
+    for rule in o.ARK_RULES:
+        make(rule)
+    o.set_ark_rule(prev)
 
 
 if __name__ == "__main__":

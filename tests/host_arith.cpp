@@ -3,13 +3,19 @@
 // Test scaffolding: never linked into libschnorr_b200.so.
 #include <cstring>
 #include <vector>
+#include "../include/schnorr_b200.h"
 #include "../schnorr_b200/csrc/wire.cuh"
+#include "../schnorr_b200/csrc/params_host.cuh"
 using namespace sb200;
 
 static fq L(const uint32_t* p) { fq r; memcpy(r.v, p, 32); return r; }
 static void S(uint32_t* p, const fq& a) { memcpy(p, a.v, 32); }
 
 extern "C" {
+// Hades tables of this build: derived from the given round constants / MDS exactly as sb200_init_ex derives them
+int h_setup_hades(const uint32_t* rc335, const uint32_t* mds25) {
+  return params::derive_hades_tables(reinterpret_cast<const uint32_t(*)[8]>(rc335), reinterpret_cast<const uint32_t(*)[5][8]>(mds25), h_hades) ? 0 : -1;
+}
 void h_counts_reset() { emu::cnt() = {}; }
 void h_counts_get(unsigned long long* o) { auto& c = emu::cnt(); o[0] = c.wide; o[1] = c.fq_mul; o[2] = c.fq_sqr; o[3] = c.fq_addsub; o[4] = c.fr_mul; o[5] = c.fq_dot5; o[6] = c.dfma; o[7] = c.fd_mul; o[8] = c.fd_sqr; o[9] = c.fd_dot5; }
 void h_fq_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { S(r, fq_mul(L(a), L(b))); }
@@ -23,6 +29,7 @@ void h_fq_inv(const uint32_t* a, uint32_t* r) { S(r, fq_inv(L(a))); }
 void h_fr_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) {
   fr x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); fr z = fr_mul(x, y); memcpy(r, z.v, 32);
 }
+#if SB_EXPERIMENTAL_FD
 // ---- FP64-pipe arithmetic (fd.cuh / hades_fd.cuh), DFMA pair emulated by a 128-bit product --------------------
 static fdd FD(const uint32_t* p) { return fd_todbl(fd_split(p)); }   // plain 256-bit integer, limbs re-sliced
 static void FS(uint32_t* p, const fd& a) { fd_join(a, p); }           // lazily reduced result (< 2^256)
@@ -44,18 +51,27 @@ void h_hades_fd(uint32_t* st) {  // Montgomery-256 words in, canonical integers 
   hades_perm_fd(s);
   for (int i = 0; i < 5; i++) fd_to_canonical(s[i], st + 8 * i);
 }
+#endif
 void h_challenge3(const uint32_t* ru, const uint32_t* rv, const uint32_t* m, int fdpath, uint32_t* c) {
+#if SB_EXPERIMENTAL_FD
   double slots[FDH_SLOTS * 10 * 3];
-  if (fdpath == 2) challenge3_fd_p(L(ru), L(rv), L(m), c, slots, 1);
-  else if (fdpath == 3) challenge3_fd_p(L(ru), L(rv), L(m), c, slots + 1, 3);  // strided layout
-  else if (fdpath) challenge3_fd(L(ru), L(rv), L(m), c); else challenge3(L(ru), L(rv), L(m), c);
+  if (fdpath == 2) { challenge3_fd_p(L(ru), L(rv), L(m), c, slots, 1); return; }
+  if (fdpath == 3) { challenge3_fd_p(L(ru), L(rv), L(m), c, slots + 1, 3); return; }  // strided layout
+  if (fdpath) { challenge3_fd(L(ru), L(rv), L(m), c); return; }
+#endif
+  challenge3(L(ru), L(rv), L(m), c);
 }
+#if SB_EXPERIMENTAL_FD
 void h_challenge3_pair(const uint32_t* ru, const uint32_t* rv, const uint32_t* m, uint32_t* c) {  // 2 x (8 words) each
   fq a[2] = {L(ru), L(ru + 8)}, b[2] = {L(rv), L(rv + 8)}, mm[2] = {L(m), L(m + 8)};
   challenge3_fd2(a, b, mm, reinterpret_cast<uint32_t(*)[8]>(c));
 }
+#endif
 void h_challenge5(const uint32_t* ru, const uint32_t* rv, const uint32_t* rpu, const uint32_t* rpv, const uint32_t* m, int fdpath, uint32_t* c) {
-  if (fdpath) challenge5_fd(L(ru), L(rv), L(rpu), L(rpv), L(m), c); else challenge5(L(ru), L(rv), L(rpu), L(rpv), L(m), c);
+#if SB_EXPERIMENTAL_FD
+  if (fdpath) { challenge5_fd(L(ru), L(rv), L(rpu), L(rpv), L(m), c); return; }
+#endif
+  challenge5(L(ru), L(rv), L(rpu), L(rpv), L(m), c);
 }
 void h_hades(uint32_t* st, int dense) {
   fq s[5]; for (int i = 0; i < 5; i++) s[i] = L(st + 8 * i);
@@ -91,6 +107,7 @@ void h_sign_double(const uint32_t* sk, const uint32_t* nonce, const uint32_t* m,
 void h_sign_vargen(const uint32_t* sk, const uint32_t* gen, int affine, const uint32_t* nonce, const uint32_t* m, uint32_t* u, uint32_t* Ruv, uint32_t* c) {
   fq a, b; sign_vargen_core(sk, P(gen, affine), nonce, L(m), u, a, b, c); S(Ruv, a); S(Ruv + 8, b);
 }
+int h_point_well_formed(const uint32_t* p, int affine) { return point_well_formed(P(p, affine)); }
 int h_decompress(const uint32_t* b, uint32_t* uv) { fq u, v; bool ok = point_decompress(b, u, v); S(uv, u); S(uv + 8, v); return ok; }
 void h_compress(const uint32_t* uv, uint32_t* b) { point_compress(L(uv), L(uv + 8), b); }
 void h_fr_from_wide(const uint32_t* w, uint32_t* r) { fr_from_wide(w, r); }

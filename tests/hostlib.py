@@ -13,13 +13,31 @@ RADIX = 1 << 256
 def build():
     so = os.path.join(ROOT, "build", "host_arith.so")
     src = os.path.join(ROOT, "tests", "host_arith.cpp")
-    hdrs = [os.path.join(ROOT, "schnorr_b200", "csrc", f) for f in ("fq.cuh", "fd.cuh", "ed.cuh", "hades.cuh", "hades_fd.cuh", "core.cuh", "wire.cuh", "constants_gen.cuh")]
+    hdrs = [os.path.join(ROOT, "schnorr_b200", "csrc", f) for f in (
+        "fq.cuh", "experimental/fd.cuh", "ed.cuh", "hades.cuh", "experimental/hades_fd.cuh", "core.cuh", "wire.cuh", "hgcd.cuh",
+        "params_host.cuh", "constants_gen.cuh", "experimental/constants_fd_gen.cuh")]
     newest = max(os.path.getmtime(p) for p in [src] + hdrs)
     if not os.path.exists(so) or os.path.getmtime(so) < newest:
         os.makedirs(os.path.dirname(so), exist_ok=True)
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-include",
+        # SB_EXPERIMENTAL_FD=1: the host tests also cover the compiled-out FP64-pipe arithmetic
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DSB_EXPERIMENTAL_FD=1", "-include",
                                os.path.join(ROOT, "tests", "host_shim.h"), "-o", so, src])
-    return ctypes.CDLL(so)
+    lib = ctypes.CDLL(so)
+    setup_hades(lib)
+    return lib
+
+
+def setup_hades(lib, rule=None):
+    """Hand the oracle's round constants / MDS (current rule, or `rule`) to the host build, which derives its sparse
+    tables from them the way sb200_init_ex does."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import schnorr_oracle as o
+    if rule is not None and rule != o.ARK_RULE:
+        o.set_ark_rule(rule)
+    rc = np.stack([mont(c) for c in o.ROUND_CONSTANTS[:335]])
+    mds = np.stack([mont(o.MDS[i][j]) for i in range(5) for j in range(5)])
+    assert lib.h_setup_hades(ptr(rc), ptr(mds)) == 0
 
 
 def limbs(x):

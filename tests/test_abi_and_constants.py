@@ -79,10 +79,7 @@ def test_generated_constants_match_oracle():
     assert one_line("SB200_ED_D_INIT") == mont(o.D) and one_line("SB200_ED_2D_INIT") == mont(2 * o.D % Q)
     assert (one_line("SB200_G_U_INIT"), one_line("SB200_G_V_INIT")) == (mont(o.G[0]), mont(o.G[1]))
     assert (one_line("SB200_GP_U_INIT"), one_line("SB200_GP_V_INIT")) == (mont(o.G_NUMS[0]), mont(o.G_NUMS[1]))
-    rc = _parse("SB200_HADES_RC_INIT", text)
-    assert rc == [mont(c) for c in o.ROUND_CONSTANTS[:335]]
-    mds = _parse("SB200_HADES_MDS_INIT", text)
-    assert mds == [mont(o.MDS[i][j]) for i in range(5) for j in range(5)]
+    assert "SB200_HADES_RC_INIT" not in text and "SB200_HADES_MDS_INIT" not in text  # inputs of sb200_init_ex now (test_params.py)
     ninv = int(re.search(r"#define SB200_FR_NINV 0x([0-9a-f]+)u", text).group(1), 16)
     assert (ninv * R + 1) % (1 << 32) == 0
 

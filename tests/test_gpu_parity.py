@@ -47,7 +47,7 @@ def test_fr_mul(engine):
     assert V.ints_out(engine.dbg_fr_mul(V.scalars(xs), V.scalars(ys))) == [x * y % R for x, y in zip(xs, ys)]
 
 
-@pytest.mark.parametrize("dense", [True, False, 2], ids=["dense", "sparse", "fd"])
+@pytest.mark.parametrize("dense", [True, False], ids=["dense", "sparse"])
 def test_hades(engine, dense):
     rnd = random.Random(14)
     states = [[0] * 5, [1] * 5, [Q - 1] * 5, [0, 1, 2, 3, 4]] + [[rnd.randrange(Q) for _ in range(5)] for _ in range(60)]
@@ -142,11 +142,10 @@ def corrupt_single(rnd, i, pk, u, Rp, m, pks):
     return pk, u, Rp, m
 
 
-@pytest.mark.parametrize("dual_pipe", [False, True], ids=["single-role", "dual-pipe"])
 @pytest.mark.parametrize("affine", [True, False])
-def test_verify_single(engine, affine, dual_pipe):
+def test_verify_single(engine, affine):
     rnd = random.Random(19)
-    n = 257 + (256 if dual_pipe else 0)  # ragged: not a multiple of 32 (dual-pipe: more than one 256-tuple tile)
+    n = 257  # ragged: not a multiple of 32
     sk, nonce, m = make_single(rnd, n)
     pks = [V.mul(o.G, a) for a in sk]
     sigs = [o.sign(a, b, mm, mul=V.mul) for a, b, mm in zip(sk, nonce, m)]
@@ -159,7 +158,7 @@ def test_verify_single(engine, affine, dual_pipe):
     zs1 = None if affine else [rnd.randrange(1, Q) for _ in tup]
     zs2 = None if affine else [rnd.randrange(1, Q) for _ in tup]
     ok, c = engine.verify(V.points([t[0] for t in tup], zs1), V.scalars([t[1] for t in tup]),
-                          V.points([t[2] for t in tup], zs2), V.fqs([t[3] for t in tup]), affine=affine, dual_pipe=dual_pipe)
+                          V.points([t[2] for t in tup], zs2), V.fqs([t[3] for t in tup]), affine=affine)
     assert list(ok) == exp
     assert V.ints_out(c) == [o.challenge_hash(t[2], t[3]) for t in tup]
 

@@ -1,0 +1,215 @@
+"""Robustness of the C ABI on the GPU: the full-size fallback of the half-size-scalar
+path driven deterministically, checked input points, byte-level signers rejecting non-canonical scalars, pageable
+vs pinned host buffers through the staging ring, stream switches, error returns that leave the context usable."""
+import ctypes
+import random
+
+import numpy as np
+import pytest
+
+import schnorr_oracle as o
+import vectors as V
+
+pytestmark = pytest.mark.gpu
+Q, R = o.Q, o.R
+
+
+def test_half_size_fallback_forced_on_chosen_lanes(engine):
+    """sb200_dbg_verify_ec with caller-chosen challenges: every third lane gets a c for which hgcd.cuh reports
+    `ok = false`, so each warp takes the vote and runs verify_ec_core beside the fast path; keys carry torsion."""
+    rnd = random.Random(41)
+    n = 101
+    hostile = V.hgcd_hostile_challenges(n // 3 + 1)
+    tors = V.torsion_points()
+    pk, u, Rr, cs, want = [], [], [], [], []
+    for i in range(n):
+        c = hostile[i // 3] if i % 3 == 0 else rnd.randrange(1 << 250)
+        P = V.mul(o.G, rnd.randrange(R))
+        if i % 5 == 1:
+            P = o.pt_add(P, tors[i % len(tors)])  # key outside the prime-order subgroup
+        ui = rnd.randrange(R)
+        good = o.pt_add(V.mul(o.G, ui), V.mul(P, c))
+        corrupt = i % 4 == 2
+        pk.append(P); u.append(ui); cs.append(c)
+        Rr.append(o.pt_add(good, o.G) if corrupt else good)
+        want.append(not corrupt)
+    got = engine.dbg_verify_ec(V.points(pk), V.scalars(u), V.points(Rr), V.scalars(cs))
+    assert got.tolist() == want
+    zs = [rnd.randrange(1, Q) for _ in range(n)]
+    got = engine.dbg_verify_ec(V.points(pk, zs), V.scalars(u), V.points(Rr, zs[::-1]), V.scalars(cs), affine=False)
+    assert got.tolist() == want
+
+
+def test_points_check_and_check_points_flag(engine):
+    rnd = random.Random(42)
+    n = 64
+    sk, nonce, msg = ([rnd.randrange(R) for _ in range(n)] for _ in range(3))
+    msg = [m % Q for m in msg]
+    pk = [V.mul(o.G, a) for a in sk]
+    sig = [o.sign(a, b, m, mul=V.mul) for a, b, m in zip(sk, nonce, msg)]
+    bad_pk = list(pk)
+    off = set(range(3, n, 7))
+    for i in off:
+        bad_pk[i] = (pk[i][0], (pk[i][1] + 1) % Q)  # off the curve
+        assert not o.on_curve(bad_pk[i])
+    assert engine.points_check(V.points(bad_pk)).tolist() == [i not in off for i in range(n)]
+    # projective: Z = 0 is rejected, any other Z accepted
+    zs = [rnd.randrange(1, Q) for _ in range(n)]
+    proj = V.points(pk, zs)
+    proj[5, 16:24] = 0
+    assert engine.points_check(proj, affine=False).tolist() == [i != 5 for i in range(n)]
+    u, Rr = V.scalars([s[0] for s in sig]), V.points([s[1] for s in sig])
+    ok_plain, _ = engine.verify(V.points(pk), u, Rr, V.fqs(msg))
+    ok_chk, _ = engine.verify(V.points(bad_pk), u, Rr, V.fqs(msg), check_points=True)
+    assert ok_plain.all() and ok_chk.tolist() == [i not in off for i in range(n)]
+    bad_R = V.points([s[1] for s in sig]).copy()
+    bad_R[9, 8:16] = V.mont(5)
+    ok_chk, _ = engine.verify(V.points(pk), u, bad_R, V.fqs(msg), check_points=True)
+    assert ok_chk.tolist() == [i != 9 for i in range(n)]
+    # the other two schemes
+    pkp = [V.mul(o.G_NUMS, a) for a in sk]
+    sd = [o.sign_double(a, b, m, mul=V.mul) for a, b, m in zip(sk, nonce, msg)]
+    bad_pkp = list(pkp)
+    bad_pkp[11] = (1, 1)
+    okd, _ = engine.verify_double(V.points(pk), V.points(bad_pkp), V.scalars([s[0] for s in sd]), V.points([s[1] for s in sd]),
+                                  V.points([s[2] for s in sd]), V.fqs(msg), check_points=True)
+    assert okd.tolist() == [i != 11 for i in range(n)]
+    gens = [V.mul(o.G, rnd.randrange(1, R)) for _ in range(n)]
+    sv = [o.sign_vargen(a, g, b, m, mul=V.mul) for a, g, b, m in zip(sk, gens, nonce, msg)]
+    pkv = [V.mul(g, a) for g, a in zip(gens, sk)]
+    bad_g = V.points(gens, zs)
+    bad_g[13, 16:24] = 0  # Z = 0
+    okv, _ = engine.verify_vargen(V.points(pkv, zs), bad_g, V.scalars([s[0] for s in sv]), V.points([s[1] for s in sv], zs),
+                                  V.fqs(msg), affine=False, check_points=True)
+    assert okv.tolist() == [i != 13 for i in range(n)]
+
+
+def _b32(xs):
+    return np.frombuffer(b"".join(int(x).to_bytes(32, "little") for x in xs), dtype=np.uint8).reshape(-1, 32)
+
+
+def test_byte_level_signers_reject_non_canonical_scalars(engine):
+    """SecretKey::from_bytes / JubJubScalar::from_bytes / BlsScalar::from_bytes -> Err(InvalidData): invalid bit set and
+    an all-zero signature, in all three signers alike; the neighbours in the same warp are untouched"""
+    rnd = random.Random(43)
+    n = 40
+    sk, nonce = [rnd.randrange(R) for _ in range(n)], [rnd.randrange(R) for _ in range(n)]
+    msg = [rnd.randrange(Q) for _ in range(n)]
+    bad = {3: "sk", 8: "nonce", 9: "nonce_huge", 17: "msg", 33: "sk_max"}
+    sk[3] = R
+    nonce[8] = R + 5
+    nonce[9] = (1 << 256) - 1  # would overflow the window recoding if it were not replaced
+    msg[17] = Q
+    sk[33] = (1 << 256) - 1
+    want_inv = [i in bad for i in range(n)]
+    sig, inv = engine.sign_bytes(_b32(sk), _b32(msg), _b32(nonce), want_invalid=True)
+    assert inv.tolist() == want_inv
+    for i in range(n):
+        if i in bad:
+            assert not sig[i].any()
+        else:
+            u, Rp, _ = o.sign(sk[i], nonce[i], msg[i], mul=V.mul)
+            assert bytes(sig[i]) == u.to_bytes(32, "little") + o.affine_to_bytes(Rp)
+    sigd, invd = engine.sign_double_bytes(_b32(sk), _b32(msg), _b32(nonce), want_invalid=True)
+    assert invd.tolist() == want_inv and all(not sigd[i].any() for i in bad)
+    u, R1, R2, _ = o.sign_double(sk[0], nonce[0], msg[0], mul=V.mul)
+    assert bytes(sigd[0]) == u.to_bytes(32, "little") + o.affine_to_bytes(R1) + o.affine_to_bytes(R2)
+    gen = V.mul(o.G, 77)
+    sk64 = np.concatenate([_b32(sk), np.tile(np.frombuffer(o.affine_to_bytes(gen), np.uint8), (n, 1))], axis=1).copy()
+    sk64[21, 32:] = np.frombuffer((2).to_bytes(32, "little"), np.uint8)  # generator that does not decode
+    sigv, okv = engine.sign_vargen_bytes(sk64, _b32(msg), _b32(nonce))
+    assert okv.tolist() == [not w and i != 21 for i, w in enumerate(want_inv)]
+    assert all(not sigv[i].any() for i in list(bad) + [21])
+    u, Rp, _ = o.sign_vargen(sk[1], gen, nonce[1], msg[1], mul=V.mul)
+    assert bytes(sigv[1]) == u.to_bytes(32, "little") + o.affine_to_bytes(Rp)
+
+
+def test_pageable_and_pinned_host_buffers_agree(engine):
+    """numpy (pageable) buffers go through the library's pinned staging ring, sb200_host_alloc buffers are copied
+    directly; several pipeline chunks either way, inputs and outputs (sign writes 96 B per tuple back)"""
+    from schnorr_b200 import POINTS_AFFINE, PinnedBuffer
+    n = 3 * (1 << 16) + 77  # chunk = 2^16: 4 chunks, the last ragged
+    rs = np.random.RandomState(5)
+    def sc(bits):
+        a = rs.randint(0, 1 << 32, size=(n, 8), dtype=np.uint64).astype(np.uint32)
+        a[:, 7] &= (1 << bits) - 1
+        return a
+    sk, nonce, msg = sc(27), sc(27), sc(30)
+    pk = engine.keygen(sk)              # pageable in, pageable out
+    u, Rr, c = engine.sign(sk, msg, nonce)
+    bufs = [PinnedBuffer(s) for s in ((n, 8), (n, 8), (n, 8), (n, 8), (n, 16), (n, 8), (n, 16), ((n + 31) // 32,))]
+    p_sk, p_msg, p_nonce, p_u, p_R, p_c, p_pk, p_bm = (b.array for b in bufs)
+    p_sk[...] = sk; p_msg[...] = msg; p_nonce[...] = nonce
+    P = lambda a: a.ctypes.data
+    engine.call("sign", n, 0, P(p_sk), P(p_msg), P(p_nonce), P(p_u), P(p_R), P(p_c))
+    engine.call("keygen", n, 0, P(p_sk), P(p_pk))
+    assert (p_u == u).all() and (p_R == Rr).all() and (p_c == c).all() and (p_pk == pk).all()
+    u2 = u.copy()
+    u2[::9, 0] ^= 1
+    p_u[...] = u2
+    p_bm[...] = 0
+    engine.call("verify", n, POINTS_AFFINE, P(p_pk), P(p_u), P(p_R), P(p_msg), P(p_bm), None)
+    ok_pinned = np.unpackbits(p_bm.view(np.uint8), bitorder="little")[:n].astype(bool)
+    ok_pageable, _ = engine.verify(pk, u2, Rr, msg, want_c=False)
+    # mixed: pinned inputs, pageable verdict bitmap
+    bm = np.zeros((n + 31) // 32 + 4, np.uint32)
+    off = (-bm.ctypes.data // 4) % 4
+    engine.call("verify", n, POINTS_AFFINE, P(p_pk), P(p_u), P(p_R), P(p_msg), bm[off:].ctypes.data, None)
+    ok_mixed = np.unpackbits(bm[off:off + (n + 31) // 32].view(np.uint8), bitorder="little")[:n].astype(bool)
+    want = (np.arange(n) % 9) != 0
+    assert (ok_pinned == want).all() and (ok_pageable == want).all() and (ok_mixed == want).all()
+    for b in bufs:
+        b.close()
+
+
+def test_device_pointer_calls_on_two_streams_are_ordered(engine):
+    """SB200_DEVICE_PTRS calls share the context's scratch rows; after sb200_set_stream the new stream waits for the
+    work enqueued on the old one, so back-to-back calls on different streams cannot overwrite each other's challenges"""
+    import torch
+    from schnorr_b200 import DEVICE_PTRS, POINTS_AFFINE
+    dev = torch.device("cuda:0")
+    n = 1 << 15
+    rs = np.random.RandomState(6)
+    def sc(bits):
+        a = rs.randint(0, 1 << 32, size=(n, 8), dtype=np.uint64).astype(np.uint32)
+        a[:, 7] &= (1 << bits) - 1
+        return a
+    batches = []
+    for k in range(2):
+        sk, nonce, msg = sc(27), sc(27), sc(30)
+        pk = engine.keygen(sk)
+        u, Rr, _ = engine.sign(sk, msg, nonce)
+        u[k::5, 0] ^= 1
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).to(dev)
+        batches.append((t(pk), t(u), t(Rr), t(msg), torch.zeros((n + 31) // 32, dtype=torch.int32, device=dev)))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    P = lambda x: x.data_ptr()
+    for rep in range(3):
+        for k, (pk, u, Rr, msg, bm) in enumerate(batches):
+            engine.set_stream(streams[k].cuda_stream)
+            engine.call("verify", n, POINTS_AFFINE | DEVICE_PTRS, P(pk), P(u), P(Rr), P(msg), P(bm), None)
+    torch.cuda.synchronize()
+    engine.set_stream(0)
+    for k, b in enumerate(batches):
+        ok = np.unpackbits(b[4].cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
+        assert (ok == ((np.arange(n) - k) % 5 != 0)).all()
+
+
+def test_errors_are_codes_and_leave_the_context_usable(engine):
+    from schnorr_b200 import SchnorrB200Error, _lib
+    a = np.zeros(8 * 64 + 4, np.uint32)
+    mis = a[1:] if a.ctypes.data % 16 == 0 else a  # a pointer that is NOT 16-byte aligned
+    while mis.ctypes.data % 16 == 0:
+        mis = mis[1:]
+    good = _lib.aligned_empty((64, 16))
+    rc = engine._lib.sb200_keygen(engine._h, 64, 0, ctypes.c_void_p(mis.ctypes.data), ctypes.c_void_p(good.ctypes.data))
+    assert rc == _lib.ERR_ARG
+    rc = engine._lib.sb200_keygen(engine._h, -1, 0, ctypes.c_void_p(good.ctypes.data), ctypes.c_void_p(good.ctypes.data))
+    assert rc == _lib.ERR_ARG
+    rc = engine._lib.sb200_verify(engine._h, 64, 0x40, None, None, None, None, None, None)  # unknown flag / null verdicts
+    assert rc == _lib.ERR_ARG
+    with pytest.raises(SchnorrB200Error):
+        engine.call("keygen", 64, 0x80, good.ctypes.data, good.ctypes.data)
+    pk = engine.keygen(V.scalars([5, 6, 7]))
+    assert V.points_out(pk) == [V.mul(o.G, k) for k in (5, 6, 7)]

@@ -314,3 +314,37 @@ def test_verify_half_size_equals_full_size(lib, tabs):
         # small-order key alone: accepts iff u G + c T == R
         Rs = o.pt_add(V.mul(o.G, u), V.mul(T, c))
         assert both(T, u, Rs, c) == (1, 1)
+
+
+def test_hostile_challenges_defeat_half_gcd_and_fallback_is_exact(lib):
+    """tests/vectors.py hgcd_hostile_challenges: the half-size path reports ok = 0 for them, and the full-size path the
+    kernel falls back to gives the oracle's verdict (the GPU twin: tests/test_gpu_robustness.py)"""
+    import ctypes
+    rnd = random.Random(77)
+    tabs = H.comb_tables(lib)
+    for c in V.hgcd_hostile_challenges(4):
+        out = np.zeros(18, np.uint32)
+        lib.h_half_gcd(H.ptr(H.limbs(c)), H.ptr(out))
+        assert out[17] == 0 and c < (1 << 250)
+        P, u = V.mul(o.G, rnd.randrange(R)), rnd.randrange(R)
+        good = o.pt_add(V.mul(o.G, u), V.mul(P, c))
+        fo = ctypes.c_int(1)
+        for Rp, want in ((good, 1), (o.pt_add(good, o.G), 0)):
+            got = lib.h_verify_ec(H.ptr(H.pt_mont(P)), H.ptr(H.limbs(u)), H.ptr(H.pt_mont(Rp)), H.ptr(H.limbs(c)), 1, H.ptr(tabs[0]), 0,
+                                  ctypes.byref(fo))
+            assert got == want
+        lib.h_verify_ec(H.ptr(H.pt_mont(P)), H.ptr(H.limbs(u)), H.ptr(H.pt_mont(good)), H.ptr(H.limbs(c)), 1, H.ptr(tabs[0]), 1, ctypes.byref(fo))
+        assert fo.value == 0
+
+
+def test_point_well_formed(lib):
+    rnd = random.Random(78)
+    for _ in range(6):
+        P = V.rand_curve_point(rnd)
+        z = rnd.randrange(1, Q)
+        assert lib.h_point_well_formed(H.ptr(H.pt_mont(P)), 1) == 1
+        assert lib.h_point_well_formed(H.ptr(H.pt_mont(P, z)), 0) == 1
+        assert lib.h_point_well_formed(H.ptr(H.pt_mont((P[0], (P[1] + 1) % Q))), 1) == 0
+        bad = H.pt_mont(P, z)
+        bad[16:24] = 0
+        assert lib.h_point_well_formed(H.ptr(bad), 0) == 0

@@ -2,6 +2,8 @@
 SURVEY.md 8(c), and agreement between its three formulations (affine ladder / fast projective / C restatement)."""
 import random
 
+import pytest
+
 import numpy as np
 
 import ref_cpu
@@ -37,8 +39,27 @@ def test_chacha_and_stdrng_known_answers():
     assert rng1.next_u64() == 14064965282130556830
 
 
-def test_poseidon_fingerprints():
-    """these pin THIS restatement (drift detection), not the un-buildable crates."""
+def test_round_constant_rules():
+    """the two recalled forms of dusk-hades' ark.bin: "cumsum" is the running sum of "plain", seeded with one"""
+    plain, cumsum = o._round_constants("plain"), o._round_constants("cumsum")
+    assert cumsum[0] == (plain[0] + 1) % Q
+    assert all(cumsum[i] == (cumsum[i - 1] + plain[i]) % Q for i in range(1, 960))
+    prev = o.set_ark_rule("plain")
+    assert o.ROUND_CONSTANTS == plain
+    o.set_ark_rule("cumsum")
+    assert o.ROUND_CONSTANTS == cumsum and o.ARK_RULE == "cumsum"
+    o.set_ark_rule(prev)
+
+
+@pytest.fixture
+def plain_rule():
+    prev = o.set_ark_rule("plain")
+    yield
+    o.set_ark_rule(prev)
+
+
+def test_poseidon_fingerprints(plain_rule):
+    """these pin THIS restatement under the "plain" rule (drift detection), not the un-buildable crates."""
     assert o.ROUND_CONSTANTS[0] == 0x4929E824CAE3E5B6915AF89C2B2EF56233518DA79404494933A12BB7322DD246
     assert o.ROUND_CONSTANTS[1] == 0x16C704062C23752559D045399F2FC29CA7DB44D857DC2A6A7385F58EBA0D4801
     assert o.ROUND_CONSTANTS[334] == 0x069D59D29D2260B3510923EE9D8845734A67B558BAFD4BE62DCFC3CF34028BE9

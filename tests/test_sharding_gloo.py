@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from schnorr_b200.sharding import bitmap_words, shard_range
+from sharding import bitmap_words, shard_range
 
 
 def test_shard_ranges_cover_and_align():

@@ -77,3 +77,24 @@ def torsion_points():
 
 
 mul = o.pt_mul_fast
+
+
+def hgcd_hostile_challenges(count, seed=5):
+    """Challenges c < 2^250 for which the half-size-scalar path (csrc/hgcd.cuh) must give up and the kernel falls back
+    to the full-size multiplication: Euclid on (8r, c) has consecutive remainders (A, s) with A >= 2^134, s < 2^121 and
+    an EVEN cofactor T on s, so neither (s, T) nor its neighbours fit the 134-bit window budget with an odd b.
+    Built backwards from A T + s T' = 8r  (T' odd, coprime to T):  c = -A / T' mod 8r."""
+    import math
+    N = 8 * R
+    rnd, out = random.Random(seed), []
+    while len(out) < count:
+        T = rnd.randrange(1 << 116, 1 << 119) & ~1
+        Tp = rnd.randrange(1, T) | 1
+        if math.gcd(T, Tp) != 1 or math.gcd(Tp, N) != 1:
+            continue
+        s = N * pow(Tp, -1, T) % T
+        A = (N - s * Tp) // T
+        c = (-A * pow(Tp, -1, N)) % N
+        if c < (1 << 250):
+            out.append(c)
+    return out

@@ -1,14 +1,25 @@
 #!/usr/bin/env python3
-"""Generate schnorr_b200/csrc/constants_gen.cuh -- every numeric constant the CUDA path uses.
+"""Generate schnorr_b200/csrc/constants_gen.cuh -- the field / curve constants the CUDA path bakes in.
 
 Product-side tool (does NOT import oracle/): the derivations are restated here so the kernels
-and the test oracle are independent.  tests/test_constants.py cross-checks the two.
+and the test oracle are independent.  tests/test_abi_and_constants.py cross-checks the two.
 
-Provenance of each block is in the emitted comments.  Field elements are emitted as 8 x u32
-little-endian limbs in Montgomery form (x * 2^256 mod p), the layout the kernels compute in and
-the same bit pattern as dusk_bls12_381::BlsScalar's internal [u64; 4] on a little-endian host.
+What is baked: the two field moduli and their Montgomery constants, the curve constant d, square-root
+tables, and the DEFAULT coordinates of the two generators.  What is NOT baked any more: the Hades round
+constants, the MDS matrix and the sparse factorisation of the partial rounds -- those are inputs of
+`sb200_init_ex` (include/schnorr_b200.h `sb200_params`) and are derived at context creation by
+csrc/params_host.cuh.  This file keeps the Python twin of that derivation (`hades_tables(rule)`), which
+tests/test_params.py compares bit-for-bit with what the library derives, and emits the tables of the
+compiled-out FP64 experiment (csrc/experimental/constants_fd_gen.cuh).
 
-Usage:  python tools/gen_constants.py            (rewrites the header in place)
+Round-constant rule (`--ark`, SURVEY.md 8(c) recall-risk item 1; both recalled from dusk-hades assets/HOWTO.md):
+    cumsum (default)  p = 1;  c_i = from_bytes_wide(SHA512^(i+1)(seed)) + p;  p = c_i
+    plain             c_i = from_bytes_wide(SHA512^(i+1)(seed))
+
+Field elements are emitted as 8 x u32 little-endian limbs in Montgomery form (x * 2^256 mod p), the layout the
+kernels compute in and the same bit pattern as dusk_bls12_381::BlsScalar's internal [u64; 4].
+
+Usage:  python tools/gen_constants.py [--ark cumsum|plain]     (rewrites the headers in place)
 """
 import hashlib
 import os
@@ -57,16 +68,30 @@ def fmt_u(x):  # integer form
 
 
 # ---- Hades252 (dusk-hades): round constants and MDS --------------------------------------
-def round_constants():
-    out, b = [], b"poseidon-for-plonk"
+ARK_RULES = ("cumsum", "plain")
+DEFAULT_ARK = "cumsum"
+
+
+def round_constants(rule=DEFAULT_ARK):
+    assert rule in ARK_RULES
+    out, b, p = [], b"poseidon-for-plonk", 1
     for _ in range(960):
         b = hashlib.sha512(b).digest()
-        out.append(int.from_bytes(b, "little") % Q)
+        c = int.from_bytes(b, "little") % Q
+        if rule == "cumsum":
+            c = (c + p) % Q
+            p = c
+        out.append(c)
     return out
 
 
 RC = round_constants()
 MDS = [[inv(i + j + WIDTH) for j in range(WIDTH)] for i in range(WIDTH)]
+
+
+def set_ark(rule):
+    global RC
+    RC = round_constants(rule)
 
 
 # ---- small exact linear algebra over F_q ---------------------------------------------------
@@ -214,8 +239,26 @@ def hades_sparse(state, sp):
     return s
 
 
+def hades_tables(rule=DEFAULT_ARK):
+    """The tables csrc/params_host.cuh derives at context creation, as Montgomery integers in the library's layout:
+    rc[335], mds[25], pre[5], sparse[59 * 11] (key, row[5], col[5] with col[P] = 0), post[25]."""
+    set_ark(rule)
+    pre_add, ks, rows, cols, post = build_sparse_partial()
+    sparse = []
+    for t in range(PARTIAL):
+        sparse += [ks[t]] + rows[t] + cols[t]
+    out = {"rc": RC[:(FULL + PARTIAL) * WIDTH], "mds": [MDS[i][j] for i in range(WIDTH) for j in range(WIDTH)],
+           "pre": pre_add, "sparse": sparse, "post": [post[i][j] for i in range(WIDTH) for j in range(WIDTH)]}
+    return {k: [mont(x) for x in v] for k, v in out.items()}
+
+
 def main():
+    import argparse
     import random
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ark", default=DEFAULT_ARK, choices=ARK_RULES)
+    rule = ap.parse_args().ark
+    set_ark(rule)
     sp = build_sparse_partial()
     rnd = random.Random(7)
     for _ in range(8):
@@ -249,7 +292,7 @@ def main():
     w("// JubJub  -u^2 + v^2 = 1 + d u^2 v^2,  d = -10240/10241 (dusk-jubjub EDWARDS_D)")
     w("#define SB200_ED_D_INIT %s" % fmt(mont(D)))
     w("#define SB200_ED_2D_INIT %s" % fmt(mont(2 * D % Q)))
-    w("// dusk_jubjub::GENERATOR and GENERATOR_NUMS, affine (u, v)")
+    w("// dusk_jubjub::GENERATOR and GENERATOR_NUMS, affine (u, v): DEFAULTS of sb200_default_params (inputs of sb200_init_ex)")
     w("#define SB200_G_U_INIT %s" % fmt(mont(G[0])))
     w("#define SB200_G_V_INIT %s" % fmt(mont(G[1])))
     w("#define SB200_GP_U_INIT %s" % fmt(mont(GP[0])))
@@ -289,37 +332,20 @@ def main():
             ex = d * 16 ** i
             w("  %s, \\" % fmt(mont(pow(ginv, ex // 2, Q) if ex % 2 == 0 else 1)))  # odd total exponent: non-residue, caught by the final check
     w("}")
-    w("// Hades252: WIDTH 5, 8 full + 59 partial rounds; round keys = SHA-512 chain over \"poseidon-for-plonk\"")
-    w("// (dusk-hades ark.bin), first 335 of 960; MDS[i][j] = 1/(i + j + 5) (dusk-hades mds.bin).")
-    w("#define SB200_HADES_NRC %d" % ((FULL + PARTIAL) * WIDTH))
-    w("#define SB200_HADES_RC_INIT { \\")
-    for c in RC[:(FULL + PARTIAL) * WIDTH]:
-        w("  %s, \\" % fmt(mont(c)))
-    w("}")
-    w("#define SB200_HADES_MDS_INIT { \\")
-    for i in range(WIDTH):
-        for j in range(WIDTH):
-            w("  %s, \\" % fmt(mont(MDS[i][j])))
-    w("}")
-    w("// Sparse factorisation of the 59 partial rounds (exact; see build_sparse_partial in the generator).")
-    w("#define SB200_HADES_PRE_INIT { \\")
-    for x in pre_add:
-        w("  %s, \\" % fmt(mont(x)))
-    w("}")
-    w("// per partial round: k (1), row (5), col (5; col[P] unused = 0)  => 11 field elements")
-    w("#define SB200_HADES_SPARSE_INIT { \\")
-    for t in range(PARTIAL):
-        w("  %s, \\" % fmt(mont(ks[t])))
-        for j in range(WIDTH):
-            w("  %s, \\" % fmt(mont(rows[t][j])))
-        for j in range(WIDTH):
-            w("  %s, \\" % fmt(mont(cols[t][j])))
-    w("}")
-    w("#define SB200_HADES_POST_INIT { \\")
-    for i in range(WIDTH):
-        for j in range(WIDTH):
-            w("  %s, \\" % fmt(mont(post[i][j])))
-    w("}")
+    w("}  // namespace sb200")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "schnorr_b200", "csrc", "constants_gen.cuh")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as f:
+        f.write("\n".join(o) + "\n")
+    print("wrote", os.path.normpath(path))
+
+    # ---- tables of the compiled-out FP64 experiment (csrc/experimental/), under the selected round-constant rule ----
+    o = []
+    w = o.append
+    w("// GENERATED by tools/gen_constants.py --ark %s -- do not edit.  Tables of the FP64-pipe experiment (SB_EXPERIMENTAL_FD)." % rule)
+    w("#pragma once")
+    w("#include <cstdint>")
+    w("namespace sb200 {")
     w("// FP64-pipe field arithmetic (csrc/fd.cuh): 5 x 52-bit limbs, Montgomery radix 2^260")
     w("#define SB200_FD_Q_D_INIT %s" % fmt_d(Q))
     w("#define SB200_FD_Q_U_INIT %s" % fmt_u(Q))
@@ -347,7 +373,7 @@ def main():
     w("// per sparse round t: the key of round t + 1 (carried by the row product), then row[0..4], col[0..3]")
     w("#define SB200_FDH_SP_ADD_INIT { \\")
     for t in range(PARTIAL):
-        w("  %s, \\" % fmt_u(m260(ks[t + 1]) if t + 1 < PARTIAL else 0))
+        w("  %s, \\" % (fmt_u(m260(ks[t + 1])) if t + 1 < PARTIAL else fmt_u(0)))
     w("}")
     w("#define SB200_FDH_SP_MAT_INIT { \\")
     for t in range(PARTIAL):
@@ -357,7 +383,7 @@ def main():
             w("  %s, \\" % fmt_d(m260(cols[t][j])))
     w("}")
     w("}  // namespace sb200")
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "schnorr_b200", "csrc", "constants_gen.cuh")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "schnorr_b200", "csrc", "experimental", "constants_fd_gen.cuh")
     os.makedirs(os.path.dirname(path), exist_ok=True)
     with open(path, "w") as f:
         f.write("\n".join(o) + "\n")

@@ -17,6 +17,12 @@
 
 constexpr int CHAINS = 8;
 
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// cycles[4*cta + {0,1,2,3}] = clock64 delta, globaltimer delta (ns), %smid, unused
 template <int MODE>
 __global__ void __launch_bounds__(256) k(uint32_t* out, long long* cycles, uint32_t seed, int ITERS) {
   uint32_t a = seed + threadIdx.x, b = seed * 2654435761u + blockIdx.x;
@@ -32,6 +38,7 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, long long* cycles, uint3
     d[i] = 1.0 + 1e-3 * (double)(x[i] & 1023);
     w[2 * i] = x[i] * 3u; w[2 * i + 1] = x[i] ^ b;
   }
+  unsigned long long g0 = gtimer();
   long long t0 = clock64();
 #pragma unroll (MODE == 7 ? 1 : 8)
   for (int it = 0; it < ITERS; it++) {
@@ -125,46 +132,69 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, long long* cycles, uint3
     }
   }
   long long t1 = clock64();
+  unsigned long long g1 = gtimer();
   uint32_t acc = 0;
 #pragma unroll
   for (int i = 0; i < CHAINS; i++) acc ^= w[2 * i] ^ w[2 * i + 1] ^ x[i] ^ (uint32_t)v[i] ^ (uint32_t)(v[i] >> 32) ^ (uint32_t)__double2loint(d[i]);
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
-  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    cycles[4 * blockIdx.x] = t1 - t0;
+    cycles[4 * blockIdx.x + 1] = (long long)(g1 - g0);
+    cycles[4 * blockIdx.x + 2] = smid;
+  }
 }
 
+// One wave: grid = SMs x resident CTAs, every CTA resident for the whole launch and doing identical work, so
+//   results/clk/SM = ops per thread x threads per SM / (clock64 delta of a CTA)            [SM-clock domain]
+//   SM clock held  = clock64 delta / globaltimer delta                                      [measured in the kernel]
+//   results/s      = total ops / CUDA-event time of the launch                              [wall domain]
+// `target_ms` sizes the launch (>= 1 s for the committed numbers: long enough that the clock record is the
+// clock under sustained load, not a boost transient).
 template <int MODE>
-int run(const char* name, double ops_per_iter, int nsm, int ctas_per_sm, uint32_t* out, long long* cyc, bool last, int ITERS) {
-  int grid = nsm * ctas_per_sm, block = 256;
-  for (int w = 0; w < 2; w++) k<MODE><<<grid, block>>>(out, cyc, 12345u + w, ITERS);
-  CK(cudaDeviceSynchronize());
+int run(const char* name, double ops_per_iter, int nsm, int /*unused*/, uint32_t* out, long long* cyc, bool last, int target_ms) {
+  int block = 256, resident = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k<MODE>, block, 0));
+  if (MODE == 7 && resident > 4) resident = 4;  // the library's kernels run 4 CTAs x 128 threads; same warps/SM here: 4 x 256 / 2
+  int grid = nsm * resident;
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  CK(cudaEventRecord(e0));
-  const int REP = 5;
-  for (int r = 0; r < REP; r++) k<MODE><<<grid, block>>>(out, cyc, 999u + r, ITERS);
-  CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
-  float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= REP;
-  long long* h = (long long*)malloc(sizeof(long long) * grid);
-  CK(cudaMemcpy(h, cyc, sizeof(long long) * grid, cudaMemcpyDeviceToHost));
-  double avg = 0; for (int i = 0; i < grid; i++) avg += (double)h[i]; avg /= grid; free(h);
-  int resident = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k<MODE>, block, 0);
-  double total_ops = ops_per_iter * ITERS * (double)block * grid;
-  double per_clk_sm = ops_per_iter * ITERS * (double)block * ctas_per_sm / avg;  // thread-level results / clk / SM
-  (void)per_clk_sm;
-  // every CTA counts its own cycles; with `resident` CTAs per SM a launch is ceil(cps/resident) waves long
-  double waves = (double)((ctas_per_sm + resident - 1) / resident);
-  double sm_cycles = avg * waves;
-  printf("  \"%s\": {\"per_s\": %.4e, \"per_clk_sm\": %.2f, \"ms\": %.4f, \"sm_mhz_during\": %.0f, \"resident_ctas\": %d}%s\n", name,
-         total_ops / (ms * 1e-3), total_ops / nsm / sm_cycles, ms, sm_cycles / (ms * 1e3), resident, last ? "" : ",");
+  int iters = 1 << 12;
+  float ms = 0;
+  for (int pass = 0; pass < 3; pass++) {  // calibrate, then the measured launch
+    CK(cudaEventRecord(e0));
+    k<MODE><<<grid, block>>>(out, cyc, 999u + pass, iters);
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (pass < 2) {
+      double want = pass == 0 ? 50.0 : (double)target_ms;
+      double f = want / (ms > 1e-3 ? ms : 1e-3);
+      iters = (int)(iters * f); iters = (iters + 7) & ~7; if (iters < 8) iters = 8;
+    }
+  }
+  long long* h = (long long*)malloc(sizeof(long long) * 4 * grid);
+  CK(cudaMemcpy(h, cyc, sizeof(long long) * 4 * grid, cudaMemcpyDeviceToHost));
+  double cyc_avg = 0, cyc_max = 0, ns_avg = 0; int per_sm[1024] = {0};
+  for (int i = 0; i < grid; i++) { cyc_avg += (double)h[4 * i]; ns_avg += (double)h[4 * i + 1]; if (h[4 * i] > cyc_max) cyc_max = (double)h[4 * i]; per_sm[h[4 * i + 2] & 1023]++; }
+  cyc_avg /= grid; ns_avg /= grid;
+  int sm_lo = 1 << 30, sm_hi = 0;
+  for (int i = 0; i < nsm; i++) { if (per_sm[i] < sm_lo) sm_lo = per_sm[i]; if (per_sm[i] > sm_hi) sm_hi = per_sm[i]; }
+  free(h);
+  double total_ops = ops_per_iter * iters * (double)block * grid;
+  double per_clk_sm = ops_per_iter * iters * (double)block * resident / cyc_avg;
+  double mhz = cyc_avg / ns_avg * 1e3;
+  printf("  \"%s\": {\"per_s\": %.4e, \"per_clk_sm\": %.3f, \"ms\": %.2f, \"sm_mhz_in_kernel\": %.1f, \"resident_ctas\": %d, "
+         "\"ctas_per_sm_min_max\": [%d, %d], \"cycles_max_over_avg\": %.4f, \"per_s_from_cycles\": %.4e}%s\n", name,
+         total_ops / (ms * 1e-3), per_clk_sm, ms, mhz, resident, sm_lo, sm_hi, cyc_max / cyc_avg, per_clk_sm * nsm * mhz * 1e6, last ? "" : ",");
   return 0;
 }
 
 int main(int argc, char** argv) {
-  int ITERS = argc > 1 ? atoi(argv[1]) : (1 << 17);  // ~20-60 ms per launch: long enough for steady clocks
+  int ITERS = argc > 1 ? atoi(argv[1]) : 1000;  // target milliseconds per measured launch
   cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
   int nsm = p.multiProcessorCount, cps = 8;  // 8 CTAs x 256 thr = 64 warps/SM (full occupancy)
   uint32_t* out; long long* cyc;
-  CK(cudaMalloc(&out, sizeof(uint32_t) * nsm * cps * 256)); CK(cudaMalloc(&cyc, sizeof(long long) * nsm * cps));
+  CK(cudaMalloc(&out, sizeof(uint32_t) * nsm * cps * 256)); CK(cudaMalloc(&cyc, sizeof(long long) * 4 * nsm * cps));
   printf("{\n  \"gpu\": \"%s\", \"sms\": %d, \"clock_khz_max\": %d,\n", p.name, nsm, p.clockRate);
   if (run<0>("imad_lo", CHAINS, nsm, cps, out, cyc, false, ITERS)) return 1;
   if (run<1>("imad_hi", CHAINS, nsm, cps, out, cyc, false, ITERS)) return 1;
@@ -177,7 +207,7 @@ int main(int argc, char** argv) {
   if (run<11>("dadd", CHAINS, nsm, cps, out, cyc, false, ITERS)) return 1;
   if (run<8>("wide8_dfma4__wide", 8, nsm, cps, out, cyc, false, ITERS)) return 1;          // counts the 8 wide products
   if (run<9>("wide8_dfma4_iadd4__wide", 8, nsm, cps, out, cyc, false, ITERS)) return 1;    // counts the 8 wide products
-  if (run<7>("fq_mul_wide_products", 240, nsm, 4, out, cyc, true, ITERS / 16)) return 1;  // 2 muls x 120 products / iter
+  if (run<7>("fq_mul_wide_products", 240, nsm, 4, out, cyc, true, ITERS)) return 1;  // 2 muls x 120 products / iter
   printf("}\n");
   return 0;
 }

@@ -14,6 +14,7 @@ so16 = os.path.join(ROOT, "build", "host_arith16.so")
 subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DSB_COMB_BITS=16", "-include",
                        os.path.join(ROOT, "tests", "host_shim.h"), "-o", so16, os.path.join(ROOT, "tests", "host_arith.cpp")])
 lib = ctypes.CDLL(so16)
+H.setup_hades(lib)  # Hades tables derived from the oracle's current round constants, as sb200_init_ex does
 W, NWIN, NENT = 16, 16, (1 << 15) + 1
 tab = [np.zeros(NWIN * NENT * 24, np.uint32), np.zeros(NWIN * NENT * 24, np.uint32)]
 for t in tab:  # entry 0 of every window = identity (1, 1, 0)

@@ -51,6 +51,6 @@ n_save, n = n, nb
 timeit("verify_bytes", lambda: e.call("verify_bytes", nb, DEVICE_PTRS, P(d_pkb), P(d_sigb), P(d_msgb), P(bm2), None))
 import numpy as _np
 assert _np.unpackbits(bm2.cpu().numpy().view(_np.uint8), bitorder="little")[:nb].all(), "byte-level verify of valid signatures"
-timeit("sign_bytes", lambda: e.call("sign_bytes", nb, DEVICE_PTRS, P(d_skb), P(d_msgb), P(d_skb), P(d_sigo)))
+timeit("sign_bytes", lambda: e.call("sign_bytes", nb, DEVICE_PTRS, P(d_skb), P(d_msgb), P(d_skb), P(d_sigo), None))
 timeit("decompress", lambda: e.call("points_decompress", nb, DEVICE_PTRS, P(d_pkb), P(d_pts), P(bm2)))
 timeit("compress", lambda: e.call("points_compress", nb, fl, P(d_pts), P(d_pkb)))
