@@ -74,6 +74,13 @@ enum {
  * `from_raw_unchecked` (/root/reference/src/keys/public.rs:142,256,427).  See also sb200_points_check. */
 #define SB200_CHECK_POINTS 8u
 
+/* sb200_sign / _sign_double / _sign_vargen / _keygen*: address-oblivious scalar multiplication -- no memory address and
+ * no branch depends on the nonce or the secret key (the reference's ladder is a constant-time select).  Fixed base:
+ * 4-bit combs of G and G' staged in shared memory and read by masked scan (64 additions instead of the 16 of the
+ * default 16-bit comb, whose 50 MB table in HBM is indexed with scalar digits); variable base: the window table is
+ * scanned instead of indexed.  Same outputs bit for bit; slower (DESIGN.md 4.2 has the measured ratio). */
+#define SB200_SIGN_OBLIVIOUS 16u
+
 /* ---- scheme parameters ------------------------------------------------------------------------------------------
  * Everything numeric that dusk-schnorr takes from its un-vendored dependency crates and that cannot be checked in
  * this build environment is an INPUT of context creation:
@@ -203,6 +210,20 @@ int sb200_sign_double_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uin
 /* SecretKeyVarGen::from_bytes(sk64)?.sign(nonce, msg).to_bytes() */
 int sb200_sign_vargen_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint8_t* sk64, const uint8_t* msg32,
                             const uint8_t* nonce32, uint8_t* sig64_out, uint32_t* invalid);
+
+/* ---- PLONK witness pre-computation ---------------------------------------------------------------
+ * Signs n tuples like sb200_sign / _sign_double / _sign_vargen (scheme 0 / 1 / 2; `generator` only for 2, its layout
+ * per SB200_POINTS_* in flags) and returns, per signature, exactly the BlsScalar values the reference's circuits
+ * allocate for it -- Signature*::append (/root/reference/src/signatures.rs:97-103, 231-241, 377-383: u, R, R') and
+ * gadgets::verify_signature* (/root/reference/src/gadgets.rs:48-68, 99-130, 162-184: pk, pk', generator, msg, the
+ * challenge, s_a = u G, s_b = c PK) -- as rows of Montgomery field elements (8 x u32 each):
+ *   scheme 0, 11 per row:  u, R.u, R.v, PK.u, PK.v, m, c, SA.u, SA.v, SB.u, SB.v
+ *   scheme 1, 19 per row:  u, R, R', PK, PK', m, c, SA, SB, SA', SB'      (points as (u, v); primed = generator G')
+ *   scheme 2, 13 per row:  u, R, PK, GEN, m, c, SA, SB
+ * u and c are the signature's scalars embedded in F_q (`BlsScalar::from(JubJubScalar)`); SA + SB == R. */
+#define SB200_WITNESS_WIDTH(scheme) ((scheme) == 0 ? 11 : (scheme) == 1 ? 19 : 13)
+int sb200_sign_witness(sb200_ctx* ctx, int64_t n, uint32_t flags, int scheme, const uint32_t* sk, const uint32_t* msg,
+                       const uint32_t* nonce, const uint32_t* generator, uint32_t* rows_out);
 
 /* on-curve and Z != 0 check of n points (what SB200_CHECK_POINTS applies inside the verify calls); ok bit i = 1 if
  * point i is a well-formed curve point.  No subgroup check (the reference has none either). */

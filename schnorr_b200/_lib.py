@@ -19,6 +19,7 @@ POINTS_AFFINE = 1
 DEVICE_PTRS = 2
 VERIFY_DUAL_PIPE = 4  # sb200_verify, SB_EXPERIMENTAL_FD builds only: warp-specialised kernel (hash warps on the FP64 pipe)
 CHECK_POINTS = 8      # verify*: on-curve / Z != 0 check of every input point on the device
+SIGN_OBLIVIOUS = 16   # sign* / keygen*: no address or branch depends on the nonce / secret key (shared-memory combs, masked scans)
 ARK_CUMSUM, ARK_PLAIN, ARK_ENV = 0, 1, -1  # rules for the DEFAULT Hades round constants (include/schnorr_b200.h)
 ERR_ARG, ERR_CUDA, ERR_NODEV, ERR_NOMEM, ERR_PARAMS, ERR_BUSY = -1, -2, -3, -4, -5, -6
 
@@ -87,6 +88,7 @@ def load_library() -> ctypes.CDLL:
         "sb200_get_params": (ci, [vp, vp]),
         "sb200_params_check": (ci, [vp, u32p]),
         "sb200_points_check": (ci, [vp, i64, u32] + [u32p] * 2),
+        "sb200_sign_witness": (ci, [vp, i64, u32, ci] + [u32p] * 5),
         "sb200_dbg_verify_ec": (ci, [vp, i64, u32] + [u32p] * 5),
         "sb200_dbg_hades_tables": (ci, [vp, u32p]),
         "sb200_destroy": (None, [vp]),
@@ -130,7 +132,7 @@ def load_library() -> ctypes.CDLL:
 
 
 EXPORTED_SYMBOLS = [
-    "sb200_init_ex", "sb200_default_params", "sb200_get_params", "sb200_params_check", "sb200_points_check", "sb200_dbg_verify_ec",
+    "sb200_sign_witness", "sb200_init_ex", "sb200_default_params", "sb200_get_params", "sb200_params_check", "sb200_points_check", "sb200_dbg_verify_ec",
     "sb200_dbg_hades_tables",
     "sb200_init", "sb200_destroy", "sb200_strerror", "sb200_last_error", "sb200_device_count", "sb200_set_stream",
     "sb200_launch_count", "sb200_host_alloc", "sb200_host_free", "sb200_verify", "sb200_verify_double",
@@ -278,47 +280,47 @@ class Engine:
                   bm.ctypes.data, c.ctypes.data if want_c else None)
         return self._unpack_bits(bm, n), c
 
-    def sign(self, sk, msg, nonce):
+    def sign(self, sk, msg, nonce, oblivious=False):
         n = np.asarray(sk).size // 8
         sk, msg, nonce = _arr(sk, 8, n, "sk"), _arr(msg, 8, n, "msg"), _arr(nonce, 8, n, "nonce")
         u, R, c = aligned_empty((n, 8)), aligned_empty((n, 16)), aligned_empty((n, 8))
-        self.call("sign", n, 0, sk.ctypes.data, msg.ctypes.data, nonce.ctypes.data, u.ctypes.data, R.ctypes.data, c.ctypes.data)
+        self.call("sign", n, SIGN_OBLIVIOUS if oblivious else 0, sk.ctypes.data, msg.ctypes.data, nonce.ctypes.data, u.ctypes.data, R.ctypes.data, c.ctypes.data)
         return u, R, c
 
-    def sign_double(self, sk, msg, nonce):
+    def sign_double(self, sk, msg, nonce, oblivious=False):
         n = np.asarray(sk).size // 8
         sk, msg, nonce = _arr(sk, 8, n, "sk"), _arr(msg, 8, n, "msg"), _arr(nonce, 8, n, "nonce")
         u, R, Rp, c = aligned_empty((n, 8)), aligned_empty((n, 16)), aligned_empty((n, 16)), aligned_empty((n, 8))
-        self.call("sign_double", n, 0, sk.ctypes.data, msg.ctypes.data, nonce.ctypes.data, u.ctypes.data, R.ctypes.data,
+        self.call("sign_double", n, SIGN_OBLIVIOUS if oblivious else 0, sk.ctypes.data, msg.ctypes.data, nonce.ctypes.data, u.ctypes.data, R.ctypes.data,
                   Rp.ctypes.data, c.ctypes.data)
         return u, R, Rp, c
 
-    def sign_vargen(self, sk, gen, msg, nonce, affine=True):
+    def sign_vargen(self, sk, gen, msg, nonce, affine=True, oblivious=False):
         n = np.asarray(sk).size // 8
-        pw, fl = self._pw(affine), POINTS_AFFINE if affine else POINTS_PROJECTIVE
+        pw, fl = self._pw(affine), (POINTS_AFFINE if affine else POINTS_PROJECTIVE) | (SIGN_OBLIVIOUS if oblivious else 0)
         sk, msg, nonce, gen = _arr(sk, 8, n, "sk"), _arr(msg, 8, n, "msg"), _arr(nonce, 8, n, "nonce"), _arr(gen, pw, n, "gen")
         u, R, c = aligned_empty((n, 8)), aligned_empty((n, 16)), aligned_empty((n, 8))
         self.call("sign_vargen", n, fl, sk.ctypes.data, gen.ctypes.data, msg.ctypes.data, nonce.ctypes.data, u.ctypes.data,
                   R.ctypes.data, c.ctypes.data)
         return u, R, c
 
-    def keygen(self, sk):
+    def keygen(self, sk, oblivious=False):
         n = np.asarray(sk).size // 8
         sk = _arr(sk, 8, n, "sk")
         pk = aligned_empty((n, 16))
-        self.call("keygen", n, 0, sk.ctypes.data, pk.ctypes.data)
+        self.call("keygen", n, SIGN_OBLIVIOUS if oblivious else 0, sk.ctypes.data, pk.ctypes.data)
         return pk
 
-    def keygen_double(self, sk):
+    def keygen_double(self, sk, oblivious=False):
         n = np.asarray(sk).size // 8
         sk = _arr(sk, 8, n, "sk")
         pk, pkp = aligned_empty((n, 16)), aligned_empty((n, 16))
-        self.call("keygen_double", n, 0, sk.ctypes.data, pk.ctypes.data, pkp.ctypes.data)
+        self.call("keygen_double", n, SIGN_OBLIVIOUS if oblivious else 0, sk.ctypes.data, pk.ctypes.data, pkp.ctypes.data)
         return pk, pkp
 
-    def keygen_vargen(self, sk, gen, affine=True):
+    def keygen_vargen(self, sk, gen, affine=True, oblivious=False):
         n = np.asarray(sk).size // 8
-        pw, fl = self._pw(affine), POINTS_AFFINE if affine else POINTS_PROJECTIVE
+        pw, fl = self._pw(affine), (POINTS_AFFINE if affine else POINTS_PROJECTIVE) | (SIGN_OBLIVIOUS if oblivious else 0)
         sk, gen = _arr(sk, 8, n, "sk"), _arr(gen, pw, n, "gen")
         pk = aligned_empty((n, 16))
         self.call("keygen_vargen", n, fl, sk.ctypes.data, gen.ctypes.data, pk.ctypes.data)
@@ -422,6 +424,22 @@ class Engine:
         bm = aligned_empty(((n + 31) // 32,)); bm[...] = 0
         self.call("sign_vargen_bytes", n, 0, sk.ctypes.data, msg.ctypes.data, nonce.ctypes.data, out.ctypes.data, bm.ctypes.data)
         return out, ~self._unpack_bits(bm, n)
+
+    WITNESS_WIDTH = (11, 19, 13)
+
+    def sign_witness(self, scheme: int, sk, msg, nonce, gen=None, affine=True):
+        """PLONK witness rows of n signatures ([n, W, 8] Montgomery limbs; W = 11 / 19 / 13 for scheme 0 single,
+        1 double, 2 vargen): u, R(, R'), PK(, PK' | GEN), m, c, SA = u G, SB = c PK(, SA', SB')"""
+        n = np.asarray(sk).size // 8
+        sk, msg, nonce = _arr(sk, 8, n, "sk"), _arr(msg, 8, n, "msg"), _arr(nonce, 8, n, "nonce")
+        fl = (POINTS_AFFINE if affine else POINTS_PROJECTIVE) if scheme == 2 else 0
+        g = _arr(gen, self._pw(affine), n, "gen") if scheme == 2 else None
+        w = self.WITNESS_WIDTH[scheme]
+        out = aligned_empty((n, w, 8))
+        rc = self._lib.sb200_sign_witness(self._h, n, fl, scheme, sk.ctypes.data, msg.ctypes.data, nonce.ctypes.data,
+                                          g.ctypes.data if g is not None else None, out.ctypes.data)
+        self._check(rc, "sign_witness")
+        return out
 
     def points_check(self, points, affine=True):
         """ok[n]: point i is on the curve with Z != 0 (what CHECK_POINTS applies inside the verify calls)"""

@@ -370,6 +370,17 @@ SB_HD ext var_base_mul(const point_in& P, const uint32_t* k) {
   return p1p1_to_ext(ed_mul_var(tab, kr, 64));
 }
 
+// k * P with the window table scanned instead of indexed (SB200_SIGN_OBLIVIOUS: k is a nonce or a secret key)
+SB_HD ext var_base_mul_oblivious(const point_in& P, const uint32_t* k) {
+  uint32_t kr[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) kr[i] = k[i];
+  recode_offset<4>(kr);
+  pniels tab[9];
+  vartable_build(tab, point_to_ext(P));
+  return p1p1_to_ext(ed_mul_var_oblivious(tab, kr));
+}
+
 SB_HD void sign_core(const uint32_t* sk, const uint32_t* nonce, const fq& m, const uint32_t* combG, uint32_t* u_out,
                      fq& Ru, fq& Rv, uint32_t* c_out) {
   ext_to_affine(fixed_base_mul(combG, nonce), Ru, Rv);
@@ -389,10 +400,90 @@ SB_HD void sign_double_core(const uint32_t* sk, const uint32_t* nonce, const fq&
 }
 
 SB_HD void sign_vargen_core(const uint32_t* sk, const point_in& GEN, const uint32_t* nonce, const fq& m, uint32_t* u_out,
-                            fq& Ru, fq& Rv, uint32_t* c_out) {
-  ext_to_affine(var_base_mul(GEN, nonce), Ru, Rv);
+                            fq& Ru, fq& Rv, uint32_t* c_out, bool oblivious = false) {
+  ext_to_affine(oblivious ? var_base_mul_oblivious(GEN, nonce) : var_base_mul(GEN, nonce), Ru, Rv);
   chal3(Ru, Rv, m, c_out);
   sign_finish(nonce, c_out, sk, u_out);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// PLONK witness pre-computation.  The reference's circuits allocate, per signature,
+//   Signature::append        u as a BlsScalar witness + R as a witness point   /root/reference/src/signatures.rs:97-103,
+//                            (+ R' for the double scheme)                       231-241, 377-383
+//   gadgets::verify_signature*   pk (pk', generator) as witness points, msg, and as component outputs the challenge
+//                            c = H(...) (sponge::truncated::gadget), s_a = u * G, s_b = c * PK, and their sum,
+//                            which assert_equal_point ties to R            /root/reference/src/gadgets.rs:48-68, 99-130, 162-184
+// All of them are BlsScalar values (affine coordinates, scalars embedded in F_q).  One row per signature, Montgomery
+// limbs like every field element of the ABI:
+//   single  (11):  u, R.u, R.v, PK.u, PK.v, m, c, SA.u, SA.v, SB.u, SB.v
+//   double  (19):  u, R, R', PK, PK', m, c, SA, SB, SA', SB'            (points as (u, v))
+//   vargen  (13):  u, R, PK, GEN, m, c, SA, SB
+// SB = c * PK is obtained as R - SA (one addition instead of a 250-bit variable-base multiplication): the signer
+// knows sk, so R = SA + SB holds by construction.  Signing itself is sign*_core's; u and c are the same scalars.
+// ------------------------------------------------------------------------------------------------------------
+SB_HD fq scalar_to_bls(const uint32_t* k) {  // JubJubScalar -> BlsScalar (the integer, embedded in F_q; k < r < q)
+  fq x;
+#pragma unroll
+  for (int i = 0; i < 8; i++) x.v[i] = k[i];
+  return fq_to_mont(x);
+}
+SB_HD ext ext_sub(const ext& a, const ext& b) { return p1p1_to_ext(ed_add(a, pniels_cneg(ext_to_pniels(b), true))); }
+
+// SCHEME 0 single, 1 double, 2 vargen (GEN = the key's generator).  row: 11 / 19 / 13 field elements.
+template <int SCHEME>
+SB_HD void witness_core(const uint32_t* sk, const uint32_t* nonce, const fq& m, const point_in& GEN, const uint32_t* combG,
+                        const uint32_t* combGp, fq* row) {
+  constexpr int NB = SCHEME == 1 ? 2 : 1;  // bases
+  ext P[6];                                // per base: R, PK, then SA, SB
+  fq z[6], pre[6];
+#pragma unroll 1
+  for (int b = 0; b < NB; b++) {
+    if (SCHEME == 2) {
+      P[0] = var_base_mul(GEN, nonce);
+      P[1] = var_base_mul(GEN, sk);
+    } else {
+      P[2 * b] = fixed_base_mul(b ? combGp : combG, nonce);
+      P[2 * b + 1] = fixed_base_mul(b ? combGp : combG, sk);
+    }
+  }
+  int np = 2 * NB;
+#pragma unroll 1
+  for (int k = 0; k < np; k++) z[k] = P[k].Z;
+  if (SCHEME == 2) z[np++] = GEN.affine ? fq_one() : GEN.Z;
+  batch_inverse(z, pre, np);
+  fq A[6][2];  // affine R, PK (, R', PK')
+#pragma unroll 1
+  for (int k = 0; k < 2 * NB; k++) {
+    A[k][0] = fq_mul(P[k].X, z[k]);
+    A[k][1] = fq_mul(P[k].Y, z[k]);
+  }
+  uint32_t c[8], u[8];
+  if (SCHEME == 1) chal5(A[0][0], A[0][1], A[2][0], A[2][1], m, c); else chal3(A[0][0], A[0][1], m, c);
+  sign_finish(nonce, c, sk, u);
+  int o = 0;
+  row[o++] = scalar_to_bls(u);
+  row[o++] = A[0][0]; row[o++] = A[0][1];                              // R
+  if (SCHEME == 1) { row[o++] = A[2][0]; row[o++] = A[2][1]; }         // R'
+  row[o++] = A[1][0]; row[o++] = A[1][1];                              // PK
+  if (SCHEME == 1) { row[o++] = A[3][0]; row[o++] = A[3][1]; }         // PK'
+  if (SCHEME == 2) { row[o++] = fq_mul(GEN.U, z[2]); row[o++] = fq_mul(GEN.V, z[2]); }  // GEN (z[2] = 1/Z or 1)
+  row[o++] = m;
+  row[o++] = scalar_to_bls(c);
+  // SA = u * base, SB = R - SA
+  ext S[4];
+#pragma unroll 1
+  for (int b = 0; b < NB; b++) {
+    S[2 * b] = SCHEME == 2 ? var_base_mul(GEN, u) : fixed_base_mul(b ? combGp : combG, u);
+    S[2 * b + 1] = ext_sub(affine_to_ext(A[2 * b][0], A[2 * b][1]), S[2 * b]);
+  }
+#pragma unroll 1
+  for (int k = 0; k < 2 * NB; k++) z[k] = S[k].Z;
+  batch_inverse(z, pre, 2 * NB);
+#pragma unroll 1
+  for (int k = 0; k < 2 * NB; k++) {
+    row[o++] = fq_mul(S[k].X, z[k]);
+    row[o++] = fq_mul(S[k].Y, z[k]);
+  }
 }
 
 }  // namespace sb200

@@ -380,21 +380,108 @@ SB_HD p1p1 ed_comb_add(ext acc, const uint32_t* table, const uint32_t* k_rec) {
   return c;
 }
 
+// ------------------------------------------------------------------------------------------
+// Address-oblivious scalar multiplication (SB200_SIGN_OBLIVIOUS): the same group elements as above with no
+// memory address and no branch depending on the (secret) scalar -- the property of the reference's ladder
+// (`acc += select(identity, P, bit)`, dusk-jubjub) that the 16-bit comb gives up by indexing a 50 MB table with
+// nonce / key digits.
+//   fixed base : comb of 4-bit signed windows, 64 windows x 8 entries (1..8) x 96 B = 48 KB per generator, staged in
+//                SHARED memory; every lane reads all 8 entries of the window (same addresses in all lanes: a
+//                broadcast, conflict-free) and keeps one by mask; 64 mixed additions, no doublings.
+//   variable   : the 9-entry window table is scanned with masks instead of being indexed.
+// ------------------------------------------------------------------------------------------
+constexpr int CT_WINDOWS = 64, CT_ENTRIES = 8;
+constexpr int CT_TABLE_WORDS = CT_WINDOWS * CT_ENTRIES * 24;  // 12 288 words = 48 KB
+
+SB_HD aniels comb4_lookup_oblivious(const uint32_t* tab, int j, int d) {
+  const uint32_t neg = (uint32_t)(d >> 31);             // all ones if d < 0
+  const uint32_t idx = ((uint32_t)d ^ neg) - neg;        // |d| in 0..8
+  uint32_t w[24];
+#pragma unroll
+  for (int k = 0; k < 24; k++) w[k] = 0;
+  const uint4* base = reinterpret_cast<const uint4*>(tab) + (size_t)j * CT_ENTRIES * 6;
+#pragma unroll 1
+  for (uint32_t e = 1; e <= (uint32_t)CT_ENTRIES; e++) {
+    const uint32_t x = idx ^ e;
+    const uint32_t mask = (uint32_t)((int32_t)((x | (0u - x)) ^ 0x80000000u) >> 31);  // all ones iff idx == e
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+      const uint4 v = base[(e - 1) * 6 + q];
+      w[4 * q] |= v.x & mask; w[4 * q + 1] |= v.y & mask; w[4 * q + 2] |= v.z & mask; w[4 * q + 3] |= v.w & mask;
+    }
+  }
+  const bool zero = idx == 0;  // digit 0: the identity (1, 1, 0)
+  aniels r;
+  const fq one = fq_one();
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const uint32_t a = zero ? one.v[k] : w[k], b = zero ? one.v[k] : w[8 + k];
+    r.YpX.v[k] = neg ? b : a;   // -Q: swap (y + x, y - x) ...
+    r.YmX.v[k] = neg ? a : b;
+    r.T2d.v[k] = w[16 + k];
+  }
+  r.T2d = fq_select(r.T2d, fq_neg(r.T2d), neg != 0);  // ... and negate 2d x y
+  return r;
+}
+
+// k * B for the generator whose 4-bit comb table is `tab` (shared memory on the device); k < 2^252 canonical
+SB_HD ext fixed_base_mul_oblivious(const uint32_t* tab, const uint32_t* k) {
+  uint32_t kr[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) kr[i] = k[i];
+  recode_offset<4>(kr);
+  ext acc = ext_identity();
+#pragma unroll 1
+  for (int j = 0; j < CT_WINDOWS; j++) acc = p1p1_to_ext(ed_add(acc, comb4_lookup_oblivious(tab, j, recode_digit<4>(kr, j))));
+  return acc;
+}
+
+SB_HD pniels vartable_lookup_oblivious(const pniels* tab, int d) {
+  const uint32_t neg = (uint32_t)(d >> 31);
+  const uint32_t idx = ((uint32_t)d ^ neg) - neg;
+  pniels r;
+#pragma unroll
+  for (int k = 0; k < 8; k++) r.YpX.v[k] = r.YmX.v[k] = r.Z.v[k] = r.T2d.v[k] = 0;
+#pragma unroll 1
+  for (uint32_t e = 0; e <= 8; e++) {
+    const uint32_t x = idx ^ e;
+    const uint32_t mask = (uint32_t)((int32_t)((x | (0u - x)) ^ 0x80000000u) >> 31);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      r.YpX.v[k] |= tab[e].YpX.v[k] & mask; r.YmX.v[k] |= tab[e].YmX.v[k] & mask;
+      r.Z.v[k] |= tab[e].Z.v[k] & mask; r.T2d.v[k] |= tab[e].T2d.v[k] & mask;
+    }
+  }
+  return pniels_cneg(r, neg != 0);
+}
+
+// k * P with the table scanned, not indexed (64 windows; k < 2^252, offset-recoded for W = 4 by the caller)
+SB_HD p1p1 ed_mul_var_oblivious(const pniels* tab, const uint32_t* k_rec) {
+  p1p1 c = ed_add(ext_identity(), vartable_lookup_oblivious(tab, recode_digit<4>(k_rec, 63)));
+#pragma unroll 1
+  for (int i = 62; i >= 0; i--) {
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) c = pt_dbl(c);
+    c = ed_add(p1p1_to_ext(c), vartable_lookup_oblivious(tab, recode_digit<4>(k_rec, i)));
+  }
+  return c;
+}
+
 }  // namespace sb200
 
 namespace sb200 {
 
 // One comb-table entry: e * 2^(W*j) * B in affine Niels form (entry 0 = identity), written as 24 limbs.
 // Run once per (j, e) at context creation (init kernel) -- plain double-and-add, speed irrelevant.
-SB_HD void comb_build_entry(const fq& Bu, const fq& Bv, int j, int e, uint32_t* out24) {
+SB_HD void comb_build_entry_w(const fq& Bu, const fq& Bv, int j, int e, uint32_t* out24, const int BITS) {
   ext base = affine_to_ext(Bu, Bv);
   pniels nb = ext_to_pniels(base);
   ext acc = ext_identity();
   // scalar = e << (8*j); walk its bits MSB-first: bits 8*j+7 .. 0
 #pragma unroll 1
-  for (int bit = COMB_BITS * j + COMB_BITS - 1; bit >= 0; bit--) {
+  for (int bit = BITS * j + BITS - 1; bit >= 0; bit--) {
     acc = p1p1_to_ext(ed_dbl(acc.X, acc.Y, acc.Z));
-    int eb = bit - COMB_BITS * j;
+    int eb = bit - BITS * j;
     bool set = (eb >= 0) && ((e >> eb) & 1);
     ext sum = p1p1_to_ext(ed_add(acc, nb));
     acc.X = fq_select(acc.X, sum.X, set);
@@ -412,5 +499,8 @@ SB_HD void comb_build_entry(const fq& Bu, const fq& Bv, int j, int e, uint32_t* 
     out24[16 + i] = t2d.v[i];
   }
 }
+SB_HD void comb_build_entry(const fq& Bu, const fq& Bv, int j, int e, uint32_t* out24) { comb_build_entry_w(Bu, Bv, j, e, out24, COMB_BITS); }
+// entry of the oblivious path's 4-bit comb: e * 16^j * B, e = 1..8
+SB_HD void comb4_build_entry(const fq& Bu, const fq& Bv, int j, int e, uint32_t* out24) { comb_build_entry_w(Bu, Bv, j, e, out24, 4); }
 
 }  // namespace sb200

@@ -53,7 +53,7 @@ enum Op : int {
   OP_DECOMPRESS, OP_COMPRESS, OP_FROM_WIDE, OP_VERIFY_BYTES, OP_SIGN_BYTES, OP_CHALLENGE, OP_VERIFY_EC,
   OP_VERIFY_DOUBLE_BYTES, OP_VERIFY_VARGEN_BYTES, OP_SIGN_DOUBLE_BYTES, OP_SIGN_VARGEN_BYTES,
   OP_CHALLENGE_DOUBLE, OP_VERIFY_DOUBLE_EC, OP_CHALLENGE_VARGEN, OP_VERIFY_VARGEN_EC, OP_POINTS_CHECK, OP_DBG_VERIFY_EC,
-  OP_DECODE_VERIFY
+  OP_DECODE_VERIFY, OP_WITNESS
 };
 
 struct KArgs {
@@ -65,6 +65,8 @@ struct KArgs {
   uint32_t* bitmap;
   const uint32_t* combG;
   const uint32_t* combGp;
+  const uint32_t* comb4G;   // 4-bit combs (48 KB each) of the address-oblivious path, staged into shared memory
+  const uint32_t* comb4Gp;
   struct WsState* ws;
   int nsm;
   pniels* ec_scratch;  // window tables of k_verify_ec_p: EC_P_CTAS * nsm * TPB threads x 18 entries (per stream)
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
       if (active) stg_point(a.out[2], i, Rpu, Rpv);
     } else {  // in: sk, gen, m, nonce
       ldg_scalar(a.in[3] + i * 8, nonce);
-      sign_vargen_core(sk, ldg_point(a.in[1], i, aff), nonce, ldg_fq(a.in[2] + i * 8), u, Ru, Rv, c);
+      sign_vargen_core(sk, ldg_point(a.in[1], i, aff), nonce, ldg_fq(a.in[2] + i * 8), u, Ru, Rv, c, (a.flags & SB200_SIGN_OBLIVIOUS) != 0);
     }
     if (active) {
       stg8(a.out[0] + i * 8, u);
@@ -292,7 +294,8 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
     fq u, v;
     ldg_scalar(a.in[0] + i * 8, sk);
     if (OP == OP_KEYGEN_VARGEN) {
-      ext_to_affine(var_base_mul(ldg_point(a.in[1], i, aff), sk), u, v);
+      const point_in g = ldg_point(a.in[1], i, aff);
+      ext_to_affine((a.flags & SB200_SIGN_OBLIVIOUS) ? var_base_mul_oblivious(g, sk) : var_base_mul(g, sk), u, v);
     } else {
       ext_to_affine(fixed_base_mul(a.combG, sk), u, v);
     }
@@ -304,6 +307,22 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
     return;
   }
 
+  if (OP == OP_WITNESS) {  // in: sk, msg, nonce (, generator) -> out0: witness rows; aux = scheme
+    uint32_t sk[8], nonce[8];
+    ldg_scalar(a.in[0] + i * 8, sk);
+    ldg_scalar(a.in[2] + i * 8, nonce);
+    const fq m = ldg_fq(a.in[1] + i * 8);
+    fq row[19];
+    int w;
+    if (a.aux == 0) { witness_core<0>(sk, nonce, m, point_in(), a.combG, a.combGp, row); w = 11; }
+    else if (a.aux == 1) { witness_core<1>(sk, nonce, m, point_in(), a.combG, a.combGp, row); w = 19; }
+    else { witness_core<2>(sk, nonce, m, ldg_point(a.in[3], i, aff), a.combG, a.combGp, row); w = 13; }
+    if (active) {
+#pragma unroll 1
+      for (int k = 0; k < w; k++) stg8(a.out[0] + (i * w + k) * 8, row[k].v);
+    }
+    return;
+  }
   if (OP == OP_DBG_FQ) {
     fq x = ldg_fq(a.in[0] + i * 8), y = a.in[1] ? ldg_fq(a.in[1] + i * 8) : fq_zero(), r;
     switch (a.aux) {
@@ -569,10 +588,22 @@ __global__ void __launch_bounds__(TPB, EC_P_CTAS) k_verify_ec_p(const KArgs a, p
 #define SB_KEYGEN_K 8
 #endif
 __host__ __device__ constexpr int fixed_k(int op) { return (op == OP_KEYGEN || op == OP_KEYGEN_DOUBLE) ? SB_KEYGEN_K : SB_SIGN_K; }
-template <int OP>
-__global__ void __launch_bounds__(TPB, 4) k_fixed_batch(const KArgs a) {
+// CT = true (SB200_SIGN_OBLIVIOUS): the scalar multiples come from 4-bit combs staged in shared memory and read
+// by masked scan (ed.cuh), so no address depends on a nonce or key -- the "branch-free fixed-base comb tables staged in
+// shared memory" form; 64 additions per multiple instead of 16 (measured: DESIGN.md 4.2).
+template <int OP, bool CT = false>
+__global__ void __launch_bounds__(TPB, CT ? 2 : 4) k_fixed_batch(const KArgs a) {
   constexpr int SIGN_K = fixed_k(OP);
   constexpr bool DOUBLE = (OP == OP_SIGN_DOUBLE || OP == OP_KEYGEN_DOUBLE);
+  extern __shared__ __align__(16) uint32_t ct_tab[];  // CT: [G | G'] 4-bit combs
+  if (CT) {
+    const uint4* src[2] = {reinterpret_cast<const uint4*>(a.comb4G), reinterpret_cast<const uint4*>(a.comb4Gp)};
+    uint4* dst = reinterpret_cast<uint4*>(ct_tab);
+#pragma unroll 1
+    for (int t = 0; t < (DOUBLE ? 2 : 1); t++)
+      for (int k = threadIdx.x; k < CT_TABLE_WORDS / 4; k += TPB) dst[t * (CT_TABLE_WORDS / 4) + k] = __ldg(src[t] + k);
+    __syncthreads();
+  }
   constexpr bool SIGN = (OP == OP_SIGN || OP == OP_SIGN_DOUBLE || OP == OP_SIGN_BYTES);
   constexpr int NP = DOUBLE ? 2 * SIGN_K : SIGN_K;
   const int64_t base = (int64_t)blockIdx.x * TPB * SIGN_K + threadIdx.x;
@@ -590,10 +621,10 @@ __global__ void __launch_bounds__(TPB, 4) k_fixed_batch(const KArgs a) {
 #pragma unroll
       for (int w = 0; w < 8; w++) k[w] = lt ? k[w] : 0u;
     }
-    ext p = fixed_base_mul(a.combG, k);
+    ext p = CT ? fixed_base_mul_oblivious(ct_tab, k) : fixed_base_mul(a.combG, k);
     X[j] = p.X; Y[j] = p.Y; Z[j] = p.Z;
     if (DOUBLE) {
-      ext q = fixed_base_mul(a.combGp, k);
+      ext q = CT ? fixed_base_mul_oblivious(ct_tab + CT_TABLE_WORDS, k) : fixed_base_mul(a.combGp, k);
       X[SIGN_K + j] = q.X; Y[SIGN_K + j] = q.Y; Z[SIGN_K + j] = q.Z;
     }
   }
@@ -652,6 +683,11 @@ __global__ void __launch_bounds__(TPB, 4) k_fixed_batch(const KArgs a) {
   }
 }
 
+__global__ void __launch_bounds__(TPB) k_comb4_build(uint32_t* table, const fq bu, const fq bv) {
+  int t = blockIdx.x * TPB + threadIdx.x;
+  if (t >= CT_WINDOWS * CT_ENTRIES) return;
+  comb4_build_entry(bu, bv, t / CT_ENTRIES, t % CT_ENTRIES + 1, table + (size_t)t * 24);
+}
 __global__ void __launch_bounds__(TPB) k_comb_build(uint32_t* table, const fq bu, const fq bv) {
   int t = blockIdx.x * TPB + threadIdx.x;
   if (t >= COMB_WINDOWS * COMB_ENTRIES) return;  // 524 304 entries at 16-bit windows
@@ -676,6 +712,7 @@ struct DevCtx {
   cudaEvent_t done[2] = {nullptr, nullptr};  // end of the work enqueued for a pipeline slot
   uint32_t* combG = nullptr;
   uint32_t* combGp = nullptr;
+  uint32_t* comb4 = nullptr;  // [G | G'] 4-bit combs of the oblivious path (2 x 48 KB)
   uint8_t* arena[2] = {nullptr, nullptr};
   size_t arena_cap[2] = {0, 0};
   Stage hin[2], hout[2];
@@ -828,6 +865,21 @@ int launch(sb200_ctx* ctx, Op op, const KArgs& a, cudaStream_t st) {
     return SB200_OK;
   }
 #endif
+  if (a.flags & SB200_SIGN_OBLIVIOUS) {
+    const size_t one = (size_t)CT_TABLE_WORDS * 4;
+    switch (op) {
+      case OP_SIGN: k_fixed_batch<OP_SIGN, true><<<gridk(OP_SIGN), TPB, one, st>>>(a); break;
+      case OP_SIGN_DOUBLE: k_fixed_batch<OP_SIGN_DOUBLE, true><<<gridk(OP_SIGN_DOUBLE), TPB, 2 * one, st>>>(a); break;
+      case OP_KEYGEN: k_fixed_batch<OP_KEYGEN, true><<<gridk(OP_KEYGEN), TPB, one, st>>>(a); break;
+      case OP_KEYGEN_DOUBLE: k_fixed_batch<OP_KEYGEN_DOUBLE, true><<<gridk(OP_KEYGEN_DOUBLE), TPB, 2 * one, st>>>(a); break;
+      case OP_SIGN_VARGEN: k_run<OP_SIGN_VARGEN><<<grid, TPB, 0, st>>>(a); break;
+      case OP_KEYGEN_VARGEN: k_run<OP_KEYGEN_VARGEN><<<grid, TPB, 0, st>>>(a); break;
+      default: return SB200_ERR_ARG;
+    }
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    CU(cudaGetLastError());
+    return SB200_OK;
+  }
   switch (op) {
 #define CASEK(O) case O: k_fixed_batch<O><<<gridk(O), TPB, 0, st>>>(a); break;
     CASEK(OP_SIGN) CASEK(OP_SIGN_DOUBLE) CASEK(OP_KEYGEN) CASEK(OP_KEYGEN_DOUBLE) CASEK(OP_SIGN_BYTES)
@@ -837,7 +889,7 @@ int launch(sb200_ctx* ctx, Op op, const KArgs& a, cudaStream_t st) {
     CASE(OP_KEYGEN_VARGEN) CASE(OP_DBG_FQ) CASE(OP_DBG_FR_MUL) CASE(OP_DBG_HADES)
     CASE(OP_DBG_SMUL) CASE(OP_DECOMPRESS) CASE(OP_COMPRESS) CASE(OP_FROM_WIDE)
     CASE(OP_SIGN_DOUBLE_BYTES) CASE(OP_SIGN_VARGEN_BYTES)
-    CASE(OP_POINTS_CHECK) CASE(OP_DBG_VERIFY_EC)
+    CASE(OP_POINTS_CHECK) CASE(OP_DBG_VERIFY_EC) CASE(OP_WITNESS)
 #undef CASE
     default: return SB200_ERR_ARG;
   }
@@ -929,6 +981,7 @@ int run_device(sb200_ctx* ctx, DevCtx& dc, const Desc& d, int64_t lo, int64_t hi
     auto carve = [](uint8_t*& q, size_t bytes) { uint8_t* r = q; q += (bytes + 63) & ~(size_t)63; return r; };
     KArgs a{};
     a.n = cn; a.flags = d.flags; a.aux = d.aux; a.combG = dc.combG; a.combGp = dc.combGp;
+    a.comb4G = dc.comb4; a.comb4Gp = dc.comb4 + CT_TABLE_WORDS;
     a.ws = dc.ws[slot]; a.nsm = dc.nsm; a.ec_scratch = dc.ec_scratch[slot];
     for (int k = 0; k < d.nin; k++) {
       if (!d.in_words[k]) continue;
@@ -996,6 +1049,9 @@ int run(sb200_ctx* ctx, int64_t n, const Desc& d) {
   uint32_t allowed = SB200_POINTS_AFFINE | SB200_DEVICE_PTRS;
   if (d.op == OP_VERIFY && SB_VERIFY_WS) allowed |= SB200_VERIFY_DUAL_PIPE;
   if (d.op == OP_VERIFY || d.op == OP_VERIFY_DOUBLE || d.op == OP_VERIFY_VARGEN) allowed |= SB200_CHECK_POINTS;
+  if (d.op == OP_SIGN || d.op == OP_SIGN_DOUBLE || d.op == OP_SIGN_VARGEN || d.op == OP_KEYGEN || d.op == OP_KEYGEN_DOUBLE ||
+      d.op == OP_KEYGEN_VARGEN)
+    allowed |= SB200_SIGN_OBLIVIOUS;
   if (d.flags & ~allowed) return SB200_ERR_ARG;
   for (int k = 0; k < d.nin; k++)
     if (d.in_words[k] && (!d.in[k] || ((uintptr_t)d.in[k] & 15))) return SB200_ERR_ARG;
@@ -1015,6 +1071,7 @@ int run(sb200_ctx* ctx, int64_t n, const Desc& d) {
     if (dc.user_ev_valid && dc.last_user_stream != st) CU(cudaStreamWaitEvent(st, dc.user_ev, 0));
     KArgs a{};
     a.n = n; a.flags = d.flags; a.aux = d.aux; a.combG = dc.combG; a.combGp = dc.combGp; a.bitmap = d.bitmap;
+    a.comb4G = dc.comb4; a.comb4Gp = dc.comb4 + CT_TABLE_WORDS;
     a.ws = dc.ws[2]; a.nsm = dc.nsm; a.ec_scratch = dc.ec_scratch[2];
     for (int k = 0; k < d.nin; k++) a.in[k] = d.in[k];
     for (int k = 0; k < d.nout; k++) a.out[k] = d.out[k];
@@ -1088,6 +1145,7 @@ void release_device(DevCtx& dc) {
   if (dc.user_ev) { if (dc.user_ev_valid) cudaEventSynchronize(dc.user_ev); cudaEventDestroy(dc.user_ev); }
   if (dc.combG) cudaFree(dc.combG);
   if (dc.combGp) cudaFree(dc.combGp);
+  if (dc.comb4) cudaFree(dc.comb4);
   for (int s = 0; s < 3; s++) {
     if (dc.ws[s]) cudaFree(dc.ws[s]);
     if (dc.ec_scratch[s]) cudaFree(dc.ec_scratch[s]);
@@ -1203,6 +1261,12 @@ int sb200_init_ex(const sb200_params* params_in, const int* devices, int n_devic
     if (cudaEventCreateWithFlags(&dc.user_ev, cudaEventDisableTiming) != cudaSuccess) return fail(SB200_ERR_CUDA);
     size_t tb = (size_t)COMB_WINDOWS * COMB_ENTRIES * 24 * 4;
     if (cudaMalloc(&dc.combG, tb) != cudaSuccess || cudaMalloc(&dc.combGp, tb) != cudaSuccess) return fail(SB200_ERR_NOMEM);
+    if (cudaMalloc(&dc.comb4, (size_t)2 * CT_TABLE_WORDS * 4) != cudaSuccess) return fail(SB200_ERR_NOMEM);
+    if (cudaFuncSetAttribute(k_fixed_batch<OP_SIGN_DOUBLE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CT_TABLE_WORDS * 4) != cudaSuccess ||
+        cudaFuncSetAttribute(k_fixed_batch<OP_KEYGEN_DOUBLE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CT_TABLE_WORDS * 4) != cudaSuccess ||
+        cudaFuncSetAttribute(k_fixed_batch<OP_SIGN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_TABLE_WORDS * 4) != cudaSuccess ||
+        cudaFuncSetAttribute(k_fixed_batch<OP_KEYGEN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_TABLE_WORDS * 4) != cudaSuccess)
+      return fail(SB200_ERR_CUDA);
     dc.nsm = prop.multiProcessorCount;
 #if SB_VERIFY_WS
     if (cudaFuncSetAttribute(k_verify_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM) != cudaSuccess) return fail(SB200_ERR_CUDA);
@@ -1217,7 +1281,9 @@ int sb200_init_ex(const sb200_params* params_in, const int* devices, int n_devic
     int grid = (COMB_WINDOWS * COMB_ENTRIES + TPB - 1) / TPB;
     k_comb_build<<<grid, TPB, 0, dc.stream[0]>>>(dc.combG, gu, gv);
     k_comb_build<<<grid, TPB, 0, dc.stream[0]>>>(dc.combGp, hu, hv);
-    ctx->launches += 2;
+    k_comb4_build<<<(CT_WINDOWS * CT_ENTRIES + TPB - 1) / TPB, TPB, 0, dc.stream[0]>>>(dc.comb4, gu, gv);
+    k_comb4_build<<<(CT_WINDOWS * CT_ENTRIES + TPB - 1) / TPB, TPB, 0, dc.stream[0]>>>(dc.comb4 + CT_TABLE_WORDS, hu, hv);
+    ctx->launches += 4;
   }
   for (auto& dc : ctx->devs)  // the table builds of all devices run concurrently
     if (cudaSetDevice(dc.dev) != cudaSuccess || cudaStreamSynchronize(dc.stream[0]) != cudaSuccess) return fail(SB200_ERR_CUDA);
@@ -1416,6 +1482,16 @@ int sb200_sign_vargen_bytes(sb200_ctx* ctx, int64_t n, uint32_t flags, const uin
   if (!sig_out || (flags & SB200_POINTS_AFFINE)) return SB200_ERR_ARG;
   Desc d; d.op = OP_SIGN_VARGEN_BYTES; d.flags = flags | SB200_POINTS_AFFINE; d.nin = 3; d.nout = 1; d.bitmap = invalid;
   IN(0, (const uint32_t*)sk, 16); IN(1, (const uint32_t*)msg, 8); IN(2, (const uint32_t*)nonce, 8); OUT(0, (uint32_t*)sig_out, 16);
+  return run(ctx, n, d);
+}
+int sb200_sign_witness(sb200_ctx* ctx, int64_t n, uint32_t flags, int scheme, const uint32_t* sk, const uint32_t* msg,
+                       const uint32_t* nonce, const uint32_t* generator, uint32_t* rows_out) {
+  if (!rows_out || scheme < 0 || scheme > 2 || (scheme == 2 && !generator)) return SB200_ERR_ARG;
+  if (scheme != 2 && (flags & SB200_POINTS_AFFINE)) return SB200_ERR_ARG;
+  static const int width[3] = {11, 19, 13};
+  Desc d; d.op = OP_WITNESS; d.flags = flags; d.aux = scheme; d.nin = 4; d.nout = 1;
+  IN(0, sk, 8); IN(1, msg, 8); IN(2, nonce, 8); IN(3, scheme == 2 ? generator : nullptr, scheme == 2 ? pt_words(flags) : 0);
+  OUT(0, rows_out, 8 * width[scheme]);
   return run(ctx, n, d);
 }
 int sb200_points_check(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* points, uint32_t* ok_bitmap) {

@@ -107,6 +107,27 @@ void h_sign_double(const uint32_t* sk, const uint32_t* nonce, const uint32_t* m,
 void h_sign_vargen(const uint32_t* sk, const uint32_t* gen, int affine, const uint32_t* nonce, const uint32_t* m, uint32_t* u, uint32_t* Ruv, uint32_t* c) {
   fq a, b; sign_vargen_core(sk, P(gen, affine), nonce, L(m), u, a, b, c); S(Ruv, a); S(Ruv + 8, b);
 }
+// PLONK witness rows (core.cuh witness_core): scheme 0 / 1 / 2 -> 11 / 19 / 13 field elements
+void h_witness(int scheme, const uint32_t* sk, const uint32_t* nonce, const uint32_t* m, const uint32_t* gen, int affine,
+               const uint32_t* combG, const uint32_t* combGp, uint32_t* rows) {
+  fq row[19];
+  const int w = scheme == 0 ? 11 : scheme == 1 ? 19 : 13;
+  if (scheme == 0) witness_core<0>(sk, nonce, L(m), point_in(), combG, combGp, row);
+  else if (scheme == 1) witness_core<1>(sk, nonce, L(m), point_in(), combG, combGp, row);
+  else witness_core<2>(sk, nonce, L(m), P(gen, affine), combG, combGp, row);
+  for (int k = 0; k < w; k++) S(rows + 8 * k, row[k]);
+}
+// address-oblivious scalar multiplication (SB200_SIGN_OBLIVIOUS): 4-bit comb read by masked scan, scanned window table
+void h_comb4_build(const uint32_t* bu, const uint32_t* bv, uint32_t* table) {  // 64 x 8 x 24 limbs
+  for (int j = 0; j < CT_WINDOWS; j++)
+    for (int e = 1; e <= CT_ENTRIES; e++) comb4_build_entry(L(bu), L(bv), j, e, table + (size_t)(j * CT_ENTRIES + e - 1) * 24);
+}
+void h_fixed_mul_oblivious(const uint32_t* comb4, const uint32_t* k, uint32_t* uv) {
+  fq a, b; ext_to_affine(fixed_base_mul_oblivious(comb4, k), a, b); S(uv, a); S(uv + 8, b);
+}
+void h_var_mul_oblivious(const uint32_t* p, int affine, const uint32_t* k, uint32_t* uv) {
+  fq a, b; ext_to_affine(var_base_mul_oblivious(P(p, affine), k), a, b); S(uv, a); S(uv + 8, b);
+}
 int h_point_well_formed(const uint32_t* p, int affine) { return point_well_formed(P(p, affine)); }
 int h_decompress(const uint32_t* b, uint32_t* uv) { fq u, v; bool ok = point_decompress(b, u, v); S(uv, u); S(uv + 8, v); return ok; }
 void h_compress(const uint32_t* uv, uint32_t* b) { point_compress(L(uv), L(uv + 8), b); }

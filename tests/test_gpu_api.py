@@ -293,3 +293,37 @@ def test_cpp_api_mirror_runs_reference_tests():
     u, Rp, _ = o.sign_vargen(sk, gen, rng.random_fr(), m, mul=V.mul)
     assert kv["vargen_generator"] == o.affine_to_bytes(gen).hex()
     assert kv["sig_vargen"] == (u.to_bytes(32, "little") + o.affine_to_bytes(Rp)).hex()
+
+
+@pytest.mark.parametrize("scheme", [0, 1, 2], ids=["single", "double", "vargen"])
+def test_sign_witness_rows_match_oracle(engine, scheme):
+    """SURVEY 8(f) row 4: the values Signature*::append and gadgets::verify_signature* allocate
+    (/root/reference/src/signatures.rs:97-103, src/gadgets.rs:48-68), one row per signature"""
+    import random
+    rnd = random.Random(60 + scheme)
+    n = 37
+    Q, R = o.Q, o.R
+    sk, nonce, msg = ([rnd.randrange(1, R) for _ in range(n)], [rnd.randrange(R) for _ in range(n)], [rnd.randrange(Q) for _ in range(n)])
+    msg[0], msg[1] = 0, Q - 1
+    gens = [V.mul(o.G, rnd.randrange(1, R)) for _ in range(n)]
+    zs = [rnd.randrange(1, Q) for _ in range(n)]
+    rows = engine.sign_witness(scheme, V.scalars(sk), V.fqs(msg), V.scalars(nonce),
+                               gen=V.points(gens, zs) if scheme == 2 else None, affine=False)
+    assert rows.shape == (n, (11, 19, 13)[scheme], 8)
+    for i in range(n):
+        got = [V.unmont(rows[i, k]) for k in range(rows.shape[1])]
+        if scheme == 0:
+            u, Rp, c = o.sign(sk[i], nonce[i], msg[i], mul=V.mul)
+            pk = V.mul(o.G, sk[i])
+            sa, sb = V.mul(o.G, u), V.mul(pk, c)
+            want = [u, *Rp, *pk, msg[i], c, *sa, *sb]
+            assert o.pt_add(sa, sb) == Rp
+        elif scheme == 1:
+            u, Rp, Rpp, c = o.sign_double(sk[i], nonce[i], msg[i], mul=V.mul)
+            pk, pkp = V.mul(o.G, sk[i]), V.mul(o.G_NUMS, sk[i])
+            want = [u, *Rp, *Rpp, *pk, *pkp, msg[i], c, *V.mul(o.G, u), *V.mul(pk, c), *V.mul(o.G_NUMS, u), *V.mul(pkp, c)]
+        else:
+            u, Rp, c = o.sign_vargen(sk[i], gens[i], nonce[i], msg[i], mul=V.mul)
+            pk = V.mul(gens[i], sk[i])
+            want = [u, *Rp, *pk, *gens[i], msg[i], c, *V.mul(gens[i], u), *V.mul(pk, c)]
+        assert got == want, (scheme, i)

@@ -213,3 +213,31 @@ def test_errors_are_codes_and_leave_the_context_usable(engine):
         engine.call("keygen", 64, 0x80, good.ctypes.data, good.ctypes.data)
     pk = engine.keygen(V.scalars([5, 6, 7]))
     assert V.points_out(pk) == [V.mul(o.G, k) for k in (5, 6, 7)]
+
+
+def test_oblivious_signing_and_keygen_match_default(engine):
+    """SB200_SIGN_OBLIVIOUS (4-bit combs in shared memory read by masked scan; scanned window tables): bit-identical
+    signatures / keys to the default path and to the oracle, for all three schemes"""
+    rnd = random.Random(44)
+    n = 300  # not a multiple of the CTA's tuple count: ragged tail
+    sk = [0, 1, R - 1] + [rnd.randrange(R) for _ in range(n - 3)]
+    nonce = [1, R - 1, 0] + [rnd.randrange(R) for _ in range(n - 3)]
+    msg = [rnd.randrange(Q) for _ in range(n)]
+    S, M, N = V.scalars(sk), V.fqs(msg), V.scalars(nonce)
+    a, b = engine.sign(S, M, N), engine.sign(S, M, N, oblivious=True)
+    assert all((x == y).all() for x, y in zip(a, b))
+    for i in (0, 1, 2, 17):
+        u, Rp, c = o.sign(sk[i], nonce[i], msg[i], mul=V.mul)
+        assert (V.to_int(b[0][i]), V.points_out(b[1][i])[0], V.to_int(b[2][i])) == (u, Rp, c)
+    a, b = engine.sign_double(S, M, N), engine.sign_double(S, M, N, oblivious=True)
+    assert all((x == y).all() for x, y in zip(a, b))
+    assert (engine.keygen(S) == engine.keygen(S, oblivious=True)).all()
+    a, b = engine.keygen_double(S), engine.keygen_double(S, oblivious=True)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+    assert V.points_out(b[1][:3]) == [V.mul(o.G_NUMS, k) for k in sk[:3]]
+    gens = [V.rand_curve_point(rnd) for _ in range(n)]  # whole curve
+    zs = [rnd.randrange(1, Q) for _ in range(n)]
+    G = V.points(gens, zs)
+    a, b = engine.sign_vargen(S, G, M, N, affine=False), engine.sign_vargen(S, G, M, N, affine=False, oblivious=True)
+    assert all((x == y).all() for x, y in zip(a, b))
+    assert (engine.keygen_vargen(S, G, affine=False) == engine.keygen_vargen(S, G, affine=False, oblivious=True)).all()

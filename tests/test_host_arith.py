@@ -348,3 +348,47 @@ def test_point_well_formed(lib):
         bad = H.pt_mont(P, z)
         bad[16:24] = 0
         assert lib.h_point_well_formed(H.ptr(bad), 0) == 0
+
+
+@pytest.mark.parametrize("scheme", [0, 1, 2])
+def test_witness_rows_host_build(lib, scheme):
+    """core.cuh witness_core on the CPU build: u, R, PK, m, c, SA = u G, SB = c PK as the gadgets allocate them"""
+    rnd = random.Random(90 + scheme)
+    tabs = H.comb_tables(lib)
+    sk, nonce, m = rnd.randrange(1, R), rnd.randrange(R), rnd.randrange(Q)
+    gen, z = V.mul(o.G, rnd.randrange(1, R)), rnd.randrange(1, Q)
+    w = (11, 19, 13)[scheme]
+    rows = np.zeros(8 * w, np.uint32)
+    lib.h_witness(scheme, H.ptr(H.limbs(sk)), H.ptr(H.limbs(nonce)), H.ptr(H.mont(m)), H.ptr(H.pt_mont(gen, z)), 0,
+                  H.ptr(tabs[0]), H.ptr(tabs[1]), H.ptr(rows))
+    got = [H.unmont(rows[8 * k:8 * k + 8]) for k in range(w)]
+    if scheme == 0:
+        u, Rp, c = o.sign(sk, nonce, m, mul=V.mul)
+        pk = V.mul(o.G, sk)
+        want = [u, *Rp, *pk, m, c, *V.mul(o.G, u), *V.mul(pk, c)]
+    elif scheme == 1:
+        u, Rp, Rpp, c = o.sign_double(sk, nonce, m, mul=V.mul)
+        pk, pkp = V.mul(o.G, sk), V.mul(o.G_NUMS, sk)
+        want = [u, *Rp, *Rpp, *pk, *pkp, m, c, *V.mul(o.G, u), *V.mul(pk, c), *V.mul(o.G_NUMS, u), *V.mul(pkp, c)]
+    else:
+        u, Rp, c = o.sign_vargen(sk, gen, nonce, m, mul=V.mul)
+        pk = V.mul(gen, sk)
+        want = [u, *Rp, *pk, *gen, m, c, *V.mul(gen, u), *V.mul(pk, c)]
+    assert got == want
+
+
+def test_oblivious_scalar_multiplication(lib):
+    """SB200_SIGN_OBLIVIOUS paths (ed.cuh): 4-bit comb read by masked scan / scanned window table give the oracle's
+    multiples for edge and random scalars"""
+    rnd = random.Random(91)
+    tab = np.zeros(64 * 8 * 24, np.uint32)
+    lib.h_comb4_build(H.ptr(H.mont(o.G[0])), H.ptr(H.mont(o.G[1])), H.ptr(tab))
+    out = np.zeros(16, np.uint32)
+    for k in [0, 1, 7, 8, 9, 15, 16, 0x88, R - 1, R, (1 << 252) - 1] + [rnd.randrange(R) for _ in range(6)]:
+        lib.h_fixed_mul_oblivious(H.ptr(tab), H.ptr(H.limbs(k)), H.ptr(out))
+        assert (H.unmont(out[:8]), H.unmont(out[8:])) == V.mul(o.G, k), hex(k)
+    P = V.rand_curve_point(rnd)  # whole curve: may carry a torsion component
+    for k in [0, 1, 8, R - 1, (1 << 252) - 1, rnd.randrange(R)]:
+        for z in (None, rnd.randrange(1, Q)):
+            lib.h_var_mul_oblivious(H.ptr(H.pt_mont(P, z)), int(z is None), H.ptr(H.limbs(k)), H.ptr(out))
+            assert (H.unmont(out[:8]), H.unmont(out[8:])) == V.mul(P, k), hex(k)
