@@ -19,12 +19,14 @@
 // BytesError{BadLength} for a wrong size; `verify` returns bool and never throws on bad signatures.
 // New relative to the reference: the `*_batch` static methods.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "schnorr_b200.h"
@@ -39,21 +41,72 @@ struct CudaError : std::runtime_error {
   using std::runtime_error::runtime_error;
 };
 
-// 16-byte aligned host vector (the ABI wants aligned buffers)
+// Aligned host vector for the ABI's arrays.  Small ones (single-tuple calls) are ordinary 64-byte aligned heap
+// memory, which the library stages through its pinned ring; batch-sized ones come from sb200_host_alloc (page-locked:
+// copied to and from the device directly, no staging pass) and are recycled through a per-thread pool, because
+// pinning memory costs far more than the batch's arithmetic.
 template <class T>
 struct avec {
   T* p = nullptr;
   size_t n = 0;
+  bool pinned = false;
+  static constexpr size_t PIN_BYTES = 1 << 16;
+  struct Pool {
+    std::vector<std::pair<void*, size_t>> free_list;
+    ~Pool() { for (auto& e : free_list) sb200_host_free(e.first); }
+  };
+  static Pool& pool() { thread_local Pool pl; return pl; }
   explicit avec(size_t count) : n(count) {
-    if (count) p = static_cast<T*>(::operator new[](count * sizeof(T), std::align_val_t(64)));
-    std::memset(p, 0, count * sizeof(T));
+    const size_t bytes = count * sizeof(T);
+    if (bytes >= PIN_BYTES) {
+      auto& fl = pool().free_list;
+      size_t best = fl.size();
+      for (size_t i = 0; i < fl.size(); i++)
+        if (fl[i].second >= bytes && (best == fl.size() || fl[i].second < fl[best].second)) best = i;
+      if (best != fl.size()) {
+        p = static_cast<T*>(fl[best].first); cap_ = fl[best].second;
+        fl.erase(fl.begin() + best);
+        pinned = true;
+      } else {
+        void* q = nullptr;
+        if (sb200_host_alloc(bytes, &q) == SB200_OK) { p = static_cast<T*>(q); cap_ = bytes; pinned = true; }
+      }
+    }
+    if (!p && count) {
+      p = static_cast<T*>(::operator new[](bytes, std::align_val_t(64)));
+      std::memset(p, 0, bytes);
+    }
   }
-  ~avec() { ::operator delete[](p, std::align_val_t(64)); }
+  ~avec() {
+    if (pinned) pool().free_list.emplace_back(p, cap_);
+    else ::operator delete[](p, std::align_val_t(64));
+  }
   avec(const avec&) = delete;
   avec& operator=(const avec&) = delete;
   T* data() { return p; }
   T& operator[](size_t i) { return p[i]; }
+
+ private:
+  size_t cap_ = 0;
 };
+
+namespace detail {
+// marshalling loops of the batch calls: split over the host's cores once a batch is large enough to pay for threads
+template <class F>
+inline void parallel_for(size_t n, F&& f) {
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t nt = n < (1u << 14) ? 1 : std::min<size_t>(hw ? hw : 1, 16);
+  if (nt <= 1) { f(0, n); return; }
+  std::vector<std::thread> th;
+  size_t per = (n + nt - 1) / nt;
+  for (size_t t = 1; t < nt; t++) {
+    size_t lo = std::min(n, t * per), hi = std::min(n, lo + per);
+    if (lo < hi) th.emplace_back([&f, lo, hi] { f(lo, hi); });
+  }
+  f(0, std::min(n, per));
+  for (auto& x : th) x.join();
+}
+}  // namespace detail
 
 // One engine per process by default (device 0); there is no CPU fallback: construction throws without a GPU.
 class Context {
@@ -94,7 +147,21 @@ class StdRng {
     return StdRng(seed);
   }
   void fill_bytes(uint8_t* out, size_t n) {
-    for (size_t i = 0; i < n; i++) {
+    size_t i = 0;
+    for (; i < n && pos_ != 64; i++) out[i] = buf_[pos_++];  // drain the current block
+    // whole blocks: ChaCha is seekable (block k depends on the key and k only), so a bulk draw -- the nonces of a
+    // batch -- is computed in parallel and still equals the sequential stream byte for byte
+    const size_t blocks = (n - i) / 64;
+    if (blocks) {
+      const uint64_t first = block_;
+      uint8_t* dst = out + i;
+      detail::parallel_for(blocks, [&](size_t lo, size_t hi) {
+        for (size_t b = lo; b < hi; b++) block(first + b, dst + 64 * b);
+      });
+      block_ += blocks;
+      i += 64 * blocks;
+    }
+    for (; i < n; i++) {
       if (pos_ == 64) refill();
       out[i] = buf_[pos_++];
     }
@@ -110,9 +177,14 @@ class StdRng {
  private:
   static uint32_t rotl(uint32_t v, int n) { return (v << n) | (v >> (32 - n)); }
   void refill() {
+    block(block_, buf_);
+    block_++;
+    pos_ = 0;
+  }
+  void block(uint64_t counter, uint8_t* out64) const {
     uint32_t st[16] = {0x61707865, 0x3320646e, 0x79622d32, 0x6b206574};
     std::memcpy(st + 4, key_, 32);
-    st[12] = (uint32_t)block_; st[13] = (uint32_t)(block_ >> 32); st[14] = st[15] = 0;
+    st[12] = (uint32_t)counter; st[13] = (uint32_t)(counter >> 32); st[14] = st[15] = 0;
     uint32_t x[16];
     std::memcpy(x, st, 64);
     auto qr = [&](int a, int b, int c, int d) {
@@ -124,9 +196,7 @@ class StdRng {
       qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14);
     }
     for (int i = 0; i < 16; i++) x[i] += st[i];
-    std::memcpy(buf_, x, 64);
-    block_++;
-    pos_ = 0;
+    std::memcpy(out64, x, 64);
   }
   uint32_t key_[8];
   uint64_t block_ = 0;
@@ -247,7 +317,7 @@ struct JubJubExtended {
 
 inline std::vector<bool> unpack_bits(const uint32_t* words, size_t n) {
   std::vector<bool> v(n);
-  for (size_t i = 0; i < n; i++) v[i] = (words[i >> 5] >> (i & 31)) & 1;
+  for (size_t i = 0; i < n; i++) v[i] = (words[i >> 5] >> (i & 31)) & 1;  // vector<bool> packs bits: not thread-safe per element
   return v;
 }
 
@@ -320,12 +390,16 @@ class SecretKey {  // /root/reference/src/keys/secret.rs:56-263
   static std::vector<Signature> sign_batch(const std::vector<SecretKey>& sks, StdRng& rng, const std::vector<BlsScalar>& msgs) {
     size_t n = sks.size();
     avec<uint32_t> sk(8 * n), m(8 * n), nonce(8 * n), u(8 * n), R(16 * n);
-    for (size_t i = 0; i < n; i++) { std::memcpy(&sk[8 * i], sks[i].s_.l, 32); std::memcpy(&m[8 * i], msgs[i].l, 32); }
+    detail::parallel_for(n, [&](size_t lo, size_t hi) {
+      for (size_t i = lo; i < hi; i++) { std::memcpy(&sk[8 * i], sks[i].s_.l, 32); std::memcpy(&m[8 * i], msgs[i].l, 32); }
+    });
     detail::wide_draws(rng, n, 0, nonce.data());
     Context& c = Context::global();
     c.check(sb200_sign(c.raw(), (int64_t)n, 0, sk.data(), m.data(), nonce.data(), u.data(), R.data(), nullptr), "sign");
     std::vector<Signature> out(n);
-    for (size_t i = 0; i < n; i++) { std::memcpy(out[i].u_.l, &u[8 * i], 32); out[i].R_ = JubJubExtended::from_affine_limbs(&R[16 * i]); }
+    detail::parallel_for(n, [&](size_t lo, size_t hi) {
+      for (size_t i = lo; i < hi; i++) { std::memcpy(out[i].u_.l, &u[8 * i], 32); out[i].R_ = JubJubExtended::from_affine_limbs(&R[16 * i]); }
+    });
     return out;
   }
   static std::vector<SignatureDouble> sign_double_batch(const std::vector<SecretKey>& sks, StdRng& rng, const std::vector<BlsScalar>& msgs) {
@@ -424,10 +498,12 @@ class PublicKey {  // /root/reference/src/keys/public.rs:59-145
                                         const std::vector<BlsScalar>& msgs) {
     size_t n = pks.size();
     avec<uint32_t> pk(24 * n), u(8 * n), R(24 * n), m(8 * n), bits((n + 31) / 32);
-    for (size_t i = 0; i < n; i++) {
-      std::memcpy(&pk[24 * i], pks[i].p_.l, 96); std::memcpy(&u[8 * i], sigs[i].u_.l, 32);
-      std::memcpy(&R[24 * i], sigs[i].R_.l, 96); std::memcpy(&m[8 * i], msgs[i].l, 32);
-    }
+    detail::parallel_for(n, [&](size_t lo, size_t hi) {
+      for (size_t i = lo; i < hi; i++) {
+        std::memcpy(&pk[24 * i], pks[i].p_.l, 96); std::memcpy(&u[8 * i], sigs[i].u_.l, 32);
+        std::memcpy(&R[24 * i], sigs[i].R_.l, 96); std::memcpy(&m[8 * i], msgs[i].l, 32);
+      }
+    });
     Context& c = Context::global();
     c.check(sb200_verify(c.raw(), (int64_t)n, SB200_POINTS_PROJECTIVE, pk.data(), u.data(), R.data(), m.data(), bits.data(), nullptr), "verify");
     return unpack_bits(bits.data(), n);

@@ -429,60 +429,64 @@ SB_HD fq scalar_to_bls(const uint32_t* k) {  // JubJubScalar -> BlsScalar (the i
 }
 SB_HD ext ext_sub(const ext& a, const ext& b) { return p1p1_to_ext(ed_add(a, pniels_cneg(ext_to_pniels(b), true))); }
 
-// SCHEME 0 single, 1 double, 2 vargen (GEN = the key's generator).  row: 11 / 19 / 13 field elements.
-template <int SCHEME>
+// SCHEME 0 single, 1 double, 2 vargen (GEN = the key's generator).  row: 11 / 19 / 13 field elements, written through
+// `emit(k, value)` as they are produced (the kernel stores straight to the output array; no per-thread row buffer).
+template <int SCHEME, class Emit>
 SB_HD void witness_core(const uint32_t* sk, const uint32_t* nonce, const fq& m, const point_in& GEN, const uint32_t* combG,
-                        const uint32_t* combGp, fq* row) {
+                        const uint32_t* combGp, Emit&& emit) {
   constexpr int NB = SCHEME == 1 ? 2 : 1;  // bases
-  ext P[6];                                // per base: R, PK, then SA, SB
-  fq z[6], pre[6];
-#pragma unroll 1
-  for (int b = 0; b < NB; b++) {
-    if (SCHEME == 2) {
-      P[0] = var_base_mul(GEN, nonce);
-      P[1] = var_base_mul(GEN, sk);
-    } else {
-      P[2 * b] = fixed_base_mul(b ? combGp : combG, nonce);
-      P[2 * b + 1] = fixed_base_mul(b ? combGp : combG, sk);
+  fq Ru[NB], Rv[NB];
+  int o = 1;  // slot 0 (u) is written once the challenge is known
+  {
+    ext P[2 * NB];  // R, PK per base
+    fq z[2 * NB + 1], pre[2 * NB + 1];
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+      P[2 * b] = SCHEME == 2 ? var_base_mul(GEN, nonce) : fixed_base_mul(b ? combGp : combG, nonce);
+      P[2 * b + 1] = SCHEME == 2 ? var_base_mul(GEN, sk) : fixed_base_mul(b ? combGp : combG, sk);
+    }
+#pragma unroll
+    for (int k = 0; k < 2 * NB; k++) z[k] = P[k].Z;
+    z[2 * NB] = (SCHEME == 2 && !GEN.affine) ? GEN.Z : fq_one();
+    batch_inverse(z, pre, 2 * NB + 1);
+#pragma unroll
+    for (int b = 0; b < NB; b++) {  // R (, R')
+      Ru[b] = fq_mul(P[2 * b].X, z[2 * b]);
+      Rv[b] = fq_mul(P[2 * b].Y, z[2 * b]);
+      emit(o++, Ru[b]);
+      emit(o++, Rv[b]);
+    }
+#pragma unroll
+    for (int b = 0; b < NB; b++) {  // PK (, PK')
+      emit(o++, fq_mul(P[2 * b + 1].X, z[2 * b + 1]));
+      emit(o++, fq_mul(P[2 * b + 1].Y, z[2 * b + 1]));
+    }
+    if (SCHEME == 2) {  // GEN, affine
+      emit(o++, fq_mul(GEN.U, z[2 * NB]));
+      emit(o++, fq_mul(GEN.V, z[2 * NB]));
     }
   }
-  int np = 2 * NB;
-#pragma unroll 1
-  for (int k = 0; k < np; k++) z[k] = P[k].Z;
-  if (SCHEME == 2) z[np++] = GEN.affine ? fq_one() : GEN.Z;
-  batch_inverse(z, pre, np);
-  fq A[6][2];  // affine R, PK (, R', PK')
-#pragma unroll 1
-  for (int k = 0; k < 2 * NB; k++) {
-    A[k][0] = fq_mul(P[k].X, z[k]);
-    A[k][1] = fq_mul(P[k].Y, z[k]);
-  }
   uint32_t c[8], u[8];
-  if (SCHEME == 1) chal5(A[0][0], A[0][1], A[2][0], A[2][1], m, c); else chal3(A[0][0], A[0][1], m, c);
+  if (SCHEME == 1) chal5(Ru[0], Rv[0], Ru[NB - 1], Rv[NB - 1], m, c); else chal3(Ru[0], Rv[0], m, c);
   sign_finish(nonce, c, sk, u);
-  int o = 0;
-  row[o++] = scalar_to_bls(u);
-  row[o++] = A[0][0]; row[o++] = A[0][1];                              // R
-  if (SCHEME == 1) { row[o++] = A[2][0]; row[o++] = A[2][1]; }         // R'
-  row[o++] = A[1][0]; row[o++] = A[1][1];                              // PK
-  if (SCHEME == 1) { row[o++] = A[3][0]; row[o++] = A[3][1]; }         // PK'
-  if (SCHEME == 2) { row[o++] = fq_mul(GEN.U, z[2]); row[o++] = fq_mul(GEN.V, z[2]); }  // GEN (z[2] = 1/Z or 1)
-  row[o++] = m;
-  row[o++] = scalar_to_bls(c);
+  emit(0, scalar_to_bls(u));
+  emit(o++, m);
+  emit(o++, scalar_to_bls(c));
   // SA = u * base, SB = R - SA
-  ext S[4];
-#pragma unroll 1
+  ext S[2 * NB];
+  fq z[2 * NB], pre[2 * NB];
+#pragma unroll
   for (int b = 0; b < NB; b++) {
     S[2 * b] = SCHEME == 2 ? var_base_mul(GEN, u) : fixed_base_mul(b ? combGp : combG, u);
-    S[2 * b + 1] = ext_sub(affine_to_ext(A[2 * b][0], A[2 * b][1]), S[2 * b]);
+    S[2 * b + 1] = ext_sub(affine_to_ext(Ru[b], Rv[b]), S[2 * b]);
   }
-#pragma unroll 1
+#pragma unroll
   for (int k = 0; k < 2 * NB; k++) z[k] = S[k].Z;
   batch_inverse(z, pre, 2 * NB);
-#pragma unroll 1
+#pragma unroll
   for (int k = 0; k < 2 * NB; k++) {
-    row[o++] = fq_mul(S[k].X, z[k]);
-    row[o++] = fq_mul(S[k].Y, z[k]);
+    emit(o++, fq_mul(S[k].X, z[k]));
+    emit(o++, fq_mul(S[k].Y, z[k]));
   }
 }
 

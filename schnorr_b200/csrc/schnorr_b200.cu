@@ -312,15 +312,12 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
     ldg_scalar(a.in[0] + i * 8, sk);
     ldg_scalar(a.in[2] + i * 8, nonce);
     const fq m = ldg_fq(a.in[1] + i * 8);
-    fq row[19];
-    int w;
-    if (a.aux == 0) { witness_core<0>(sk, nonce, m, point_in(), a.combG, a.combGp, row); w = 11; }
-    else if (a.aux == 1) { witness_core<1>(sk, nonce, m, point_in(), a.combG, a.combGp, row); w = 19; }
-    else { witness_core<2>(sk, nonce, m, ldg_point(a.in[3], i, aff), a.combG, a.combGp, row); w = 13; }
-    if (active) {
-#pragma unroll 1
-      for (int k = 0; k < w; k++) stg8(a.out[0] + (i * w + k) * 8, row[k].v);
-    }
+    const int w = a.aux == 0 ? 11 : a.aux == 1 ? 19 : 13;
+    uint32_t* dst = a.out[0] + i * w * 8;
+    auto emit = [&](int k, const fq& v) { if (active) stg8(dst + k * 8, v.v); };
+    if (a.aux == 0) witness_core<0>(sk, nonce, m, point_in(), a.combG, a.combGp, emit);
+    else if (a.aux == 1) witness_core<1>(sk, nonce, m, point_in(), a.combG, a.combGp, emit);
+    else witness_core<2>(sk, nonce, m, ldg_point(a.in[3], i, aff), a.combG, a.combGp, emit);
     return;
   }
   if (OP == OP_DBG_FQ) {
@@ -885,7 +882,13 @@ int launch(sb200_ctx* ctx, Op op, const KArgs& a, cudaStream_t st) {
     CASEK(OP_SIGN) CASEK(OP_SIGN_DOUBLE) CASEK(OP_KEYGEN) CASEK(OP_KEYGEN_DOUBLE) CASEK(OP_SIGN_BYTES)
 #undef CASEK
 #define CASE(O) case O: k_run<O><<<grid, TPB, 0, st>>>(a); break;
-    CASE(OP_VERIFY) CASE(OP_VERIFY_DOUBLE) CASE(OP_VERIFY_VARGEN) CASE(OP_SIGN_VARGEN)
+#if !SB_VERIFY_SPLIT  // the fused one-launch verification kernels: only built when the split form is switched off
+    CASE(OP_VERIFY) CASE(OP_VERIFY_DOUBLE)
+#endif
+#if !(SB_VERIFY_SPLIT && SB_VARGEN_SPLIT)
+    CASE(OP_VERIFY_VARGEN)
+#endif
+    CASE(OP_SIGN_VARGEN)
     CASE(OP_KEYGEN_VARGEN) CASE(OP_DBG_FQ) CASE(OP_DBG_FR_MUL) CASE(OP_DBG_HADES)
     CASE(OP_DBG_SMUL) CASE(OP_DECOMPRESS) CASE(OP_COMPRESS) CASE(OP_FROM_WIDE)
     CASE(OP_SIGN_DOUBLE_BYTES) CASE(OP_SIGN_VARGEN_BYTES)

@@ -110,12 +110,10 @@ void h_sign_vargen(const uint32_t* sk, const uint32_t* gen, int affine, const ui
 // PLONK witness rows (core.cuh witness_core): scheme 0 / 1 / 2 -> 11 / 19 / 13 field elements
 void h_witness(int scheme, const uint32_t* sk, const uint32_t* nonce, const uint32_t* m, const uint32_t* gen, int affine,
                const uint32_t* combG, const uint32_t* combGp, uint32_t* rows) {
-  fq row[19];
-  const int w = scheme == 0 ? 11 : scheme == 1 ? 19 : 13;
-  if (scheme == 0) witness_core<0>(sk, nonce, L(m), point_in(), combG, combGp, row);
-  else if (scheme == 1) witness_core<1>(sk, nonce, L(m), point_in(), combG, combGp, row);
-  else witness_core<2>(sk, nonce, L(m), P(gen, affine), combG, combGp, row);
-  for (int k = 0; k < w; k++) S(rows + 8 * k, row[k]);
+  auto emit = [&](int k, const fq& v) { S(rows + 8 * k, v); };
+  if (scheme == 0) witness_core<0>(sk, nonce, L(m), point_in(), combG, combGp, emit);
+  else if (scheme == 1) witness_core<1>(sk, nonce, L(m), point_in(), combG, combGp, emit);
+  else witness_core<2>(sk, nonce, L(m), P(gen, affine), combG, combGp, emit);
 }
 // address-oblivious scalar multiplication (SB200_SIGN_OBLIVIOUS): 4-bit comb read by masked scan, scanned window table
 void h_comb4_build(const uint32_t* bu, const uint32_t* bv, uint32_t* table) {  // 64 x 8 x 24 limbs

@@ -269,7 +269,7 @@ def test_cpp_api_mirror_runs_reference_tests():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = os.path.join(root, "build", "test_api_cpp")
     os.makedirs(os.path.dirname(exe), exist_ok=True)
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(root, "tests", "cpp", "test_api.cpp"),
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-o", exe, os.path.join(root, "tests", "cpp", "test_api.cpp"),
                            "-L" + os.path.join(root, "schnorr_b200"), "-lschnorr_b200",
                            "-Wl,-rpath," + os.path.join(root, "schnorr_b200")])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
