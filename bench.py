@@ -548,6 +548,11 @@ def main():
     strong = None
     if world > 1 and not args.no_extras and not only:
         barrier()
+        # the other ranks wait on the HOST (TCP store), not in an NCCL barrier: a pending NCCL collective is a kernel spinning on
+        # their GPUs, which are exactly the devices rank 0's multi-device context is about to measure
+        store = dist.distributed_c10d._get_default_store()
+        if rank != 0:
+            store.wait(["sb200_strong_done"])
         if rank == 0:
             try:
                 big = Engine(list(range(world)))
@@ -567,6 +572,7 @@ def main():
                 big.close()
             except Exception as ex:  # pragma: no cover
                 strong = {"error": repr(ex)}
+            store.set("sb200_strong_done", "1")
         barrier()
 
     if rank == 0:

@@ -12,6 +12,7 @@
 #include "ed.cuh"
 #include "hades.cuh"
 #include "hgcd.cuh"
+#include "lat3.cuh"
 // The FP64-pipe permutation is a measured experiment that lost; it is compiled only with
 // -DSB_EXPERIMENTAL_FD=1 (its tables are baked by tools/gen_constants.py, not context parameters).
 #ifndef SB_EXPERIMENTAL_FD
@@ -238,10 +239,58 @@ SB_HD bool verify_vargen_ec(const point_in& PK, const point_in& GEN, const uint3
   p1p1 cp = ed_mul_var2_rolled(tabs[0], u, tabs[1], c, 64);
   return ok & p1p1_equals(cp, R);
 }
+// The same predicate with short scalars (lat3.cuh):  d Gen + a PK - b R == identity  for a lattice vector (b, a, d),
+// a = b c, d = b u (mod 8r), b odd: three variable-base tables, 44 windows (172 doublings) instead of 64 (252).
+// `fast_ok` = false where no basis vector fits the window budget; the caller then uses verify_vargen_ec.
+#ifndef SB_VARGEN_LAT3
+#define SB_VARGEN_LAT3 1
+#endif
+SB_HD bool verify_vargen_ec_fast(const point_in& PK, const point_in& GEN, const uint32_t* u_in, const point_in& R,
+                                 const uint32_t* c_in, bool& fast_ok) {
+  bool ok = scalar_lt_r(u_in);
+  uint32_t u[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) u[i] = ok ? u_in[i] : 0u;
+  lat3_res L = lattice3_8r(c_in, u);
+  fast_ok = L.ok;
+  uint32_t kr[24];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    kr[i] = L.d[i];
+    kr[8 + i] = L.a[i];
+    kr[16 + i] = L.b[i];
+  }
+  pniels tabs[27];  // multiples of sgn(d) Gen, sgn(a) PK, -sgn(b) R
+#pragma unroll 1
+  for (int t = 0; t < 3; t++) {
+    const point_in& P = t == 0 ? GEN : t == 1 ? PK : R;
+    const bool neg = t == 0 ? L.dneg : t == 1 ? L.aneg : !L.bneg;
+    vartable_build(tabs + 9 * t, point_to_ext(neg ? point_neg(P) : P));
+    recode_offset<4>(kr + 8 * t);
+  }
+  p1p1 cp = ed_mul_var3_rolled(tabs, kr, LAT3_WINDOWS);
+  // identity <=> E = 0 and H = F (see verify_ec_half)
+  return ok & fq_is_zero(cp.E) & fq_eq(cp.H, cp.F);
+}
+// u Gen + c PK == R, by the short-scalar form where it applies
+SB_HD bool verify_vargen_ec_auto(const point_in& PK, const point_in& GEN, const uint32_t* u_in, const point_in& R,
+                                 const uint32_t* c_in) {
+#if SB_VARGEN_LAT3
+  bool fast_ok;
+  bool ok = verify_vargen_ec_fast(PK, GEN, u_in, R, c_in, fast_ok);
+  if (SB_WARP_ANY(!fast_ok)) {
+    bool slow = verify_vargen_ec(PK, GEN, u_in, R, c_in);
+    ok = fast_ok ? ok : slow;
+  }
+  return ok;
+#else
+  return verify_vargen_ec(PK, GEN, u_in, R, c_in);
+#endif
+}
 SB_HD bool verify_vargen_core(const point_in& PK, const point_in& GEN, const uint32_t* u_in, const point_in& R,
                               const fq& m, uint32_t* c_out) {
   verify_hash_core(R, m, c_out);
-  return verify_vargen_ec(PK, GEN, u_in, R, c_out);
+  return verify_vargen_ec_auto(PK, GEN, u_in, R, c_out);
 }
 
 // hash half of the double-key verification: c = H(R, R', m)

@@ -338,6 +338,26 @@ SB_HD p1p1 ed_mul_var2_rolled(const pniels* tab1, const uint32_t* k1_rec, const 
   return c;
 }
 
+// Straus over THREE variable points (the variable-generator verification with short scalars, lat3.cuh):
+// tabs = 27 entries (three 9-entry tables back to back), kr = three offset-recoded scalars (8 limbs each).
+// One copy of the conversion + lookup + addition sequence, as in ed_mul_var2_rolled.
+SB_HD p1p1 ed_mul_var3_rolled(const pniels* tabs, const uint32_t* kr, int nwin) {
+  p1p1 c = ed_add(ext_identity(), vartable_lookup(tabs, recode_digit<4>(kr, nwin - 1)));
+#pragma unroll 1
+  for (int t = 1; t < 3; t++) c = ed_add(p1p1_to_ext(c), vartable_lookup(tabs + 9 * t, recode_digit<4>(kr + 8 * t, nwin - 1)));
+#pragma unroll 1
+  for (int i = nwin - 2; i >= 0; i--) {
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) c = pt_dbl(c);
+#pragma unroll 1
+    for (int t = 0; t < 3; t++) {
+      ext e = p1p1_to_ext(c);
+      c = ed_add(e, vartable_lookup(tabs + 9 * t, recode_digit<4>(kr + 8 * t, i)));
+    }
+  }
+  return c;
+}
+
 // ------------------------------------------------------------------------------------------
 // fixed-base comb.  Table layout: window j, entry e (0..2^(W-1)) = e * 2^(W*j) * B in affine Niels form,
 // entry 0 = identity; 96 bytes per entry.  acc += k * B with k offset-recoded (W = COMB_BITS).

@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
     uint32_t u[8];
     ldg_scalar(a.in[2] + i * 8, u);
     ldg_scalar(a.out[0] + i * 8, c);
-    bool ok = verify_vargen_ec(ldg_point(a.in[0], i, aff), ldg_point(a.in[1], i, aff), u, ldg_point(a.in[3], i, aff), c);
+    bool ok = verify_vargen_ec_auto(ldg_point(a.in[0], i, aff), ldg_point(a.in[1], i, aff), u, ldg_point(a.in[3], i, aff), c);
     if (a.flags & SB200_CHECK_POINTS) {
 #pragma unroll 1
       for (int k = 0; k < 4; k++)

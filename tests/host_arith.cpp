@@ -126,6 +126,18 @@ void h_fixed_mul_oblivious(const uint32_t* comb4, const uint32_t* k, uint32_t* u
 void h_var_mul_oblivious(const uint32_t* p, int affine, const uint32_t* k, uint32_t* uv) {
   fq a, b; ext_to_affine(var_base_mul_oblivious(P(p, affine), k), a, b); S(uv, a); S(uv + 8, b);
 }
+// 3-dimensional short vector for the variable-generator verification: out = a[8] | b[8] | d[8] | aneg bneg dneg ok
+void h_lattice3(const uint32_t* c, const uint32_t* u, uint32_t* out) {
+  lat3_res r = lattice3_8r(c, u);
+  memcpy(out, r.a, 32); memcpy(out + 8, r.b, 32); memcpy(out + 16, r.d, 32);
+  out[24] = r.aneg; out[25] = r.bneg; out[26] = r.dneg; out[27] = r.ok;
+}
+int h_verify_vargen_ec(const uint32_t* pk, const uint32_t* gen, const uint32_t* u, const uint32_t* R, const uint32_t* c, int affine, int fast, int* fast_ok) {
+  bool fo = true;
+  bool ok = fast ? verify_vargen_ec_fast(P(pk, affine), P(gen, affine), u, P(R, affine), c, fo) : verify_vargen_ec(P(pk, affine), P(gen, affine), u, P(R, affine), c);
+  *fast_ok = fo;
+  return ok;
+}
 int h_point_well_formed(const uint32_t* p, int affine) { return point_well_formed(P(p, affine)); }
 int h_decompress(const uint32_t* b, uint32_t* uv) { fq u, v; bool ok = point_decompress(b, u, v); S(uv, u); S(uv + 8, v); return ok; }
 void h_compress(const uint32_t* uv, uint32_t* b) { point_compress(L(uv), L(uv + 8), b); }

@@ -241,3 +241,42 @@ def test_oblivious_signing_and_keygen_match_default(engine):
     a, b = engine.sign_vargen(S, G, M, N, affine=False), engine.sign_vargen(S, G, M, N, affine=False, oblivious=True)
     assert all((x == y).all() for x, y in zip(a, b))
     assert (engine.keygen_vargen(S, G, affine=False) == engine.keygen_vargen(S, G, affine=False, oblivious=True)).all()
+
+
+def test_vargen_short_scalars_and_their_fallback(engine):
+    """csrc/lat3.cuh on the GPU: the three-table short-scalar form of PublicKeyVarGen::verify against the oracle, with
+    lanes that force the full-size fallback (u = r - 1: every short lattice vector has an even b) mixed into every
+    warp -- valid and corrupted, generators and keys with torsion components"""
+    rnd = random.Random(45)
+    n = 130
+    tors = V.torsion_points()
+    pk, gen, u, Rr, msg, want = [], [], [], [], [], []
+    for i in range(n):
+        g = V.mul(o.G, rnd.randrange(1, R))
+        m = rnd.randrange(Q)
+        if i % 4 == 0:  # forced fallback, valid by construction: PK = (k - u) / c * g for R = k g
+            ui, k = R - 1, rnd.randrange(1, R)
+            Rp = V.mul(g, k)
+            c = o.challenge_hash(Rp, m)
+            P = V.mul(g, (k - ui) * pow(c, -1, R) % R)
+        else:
+            sk, nonce = rnd.randrange(1, R), rnd.randrange(R)
+            ui, Rp, c = o.sign_vargen(sk, g, nonce, m, mul=V.mul)
+            P = V.mul(g, sk)
+        valid = True
+        if i % 3 == 1:
+            Rp = o.pt_add(Rp, g); valid = False      # wrong nonce point
+        if i % 5 == 2:
+            P = o.pt_add(P, tors[i % len(tors)])      # torsion component on the key: verdict from the oracle
+            valid = None
+        if i % 7 == 3:
+            g = o.pt_add(g, tors[(i + 1) % len(tors)])
+            valid = None
+        if valid is None:
+            valid = o.verify_vargen(P, g, ui, Rp, m, mul=V.mul)
+        pk.append(P); gen.append(g); u.append(ui); Rr.append(Rp); msg.append(m); want.append(bool(valid))
+    ok, _ = engine.verify_vargen(V.points(pk), V.points(gen), V.scalars(u), V.points(Rr), V.fqs(msg))
+    assert ok.tolist() == want and any(want) and not all(want)
+    zs = [rnd.randrange(1, Q) for _ in range(n)]
+    ok, _ = engine.verify_vargen(V.points(pk, zs), V.points(gen, zs[::-1]), V.scalars(u), V.points(Rr, zs), V.fqs(msg), affine=False)
+    assert ok.tolist() == want

@@ -392,3 +392,59 @@ def test_oblivious_scalar_multiplication(lib):
         for z in (None, rnd.randrange(1, Q)):
             lib.h_var_mul_oblivious(H.ptr(H.pt_mont(P, z)), int(z is None), H.ptr(H.limbs(k)), H.ptr(out))
             assert (H.unmont(out[:8]), H.unmont(out[8:])) == V.mul(P, k), hex(k)
+
+
+def _lat3(lib, c, u):
+    out = np.zeros(28, np.uint32)
+    lib.h_lattice3(H.ptr(H.limbs(c)), H.ptr(H.limbs(u)), H.ptr(out))
+    a, b, d = H.to_int(out[:8]), H.to_int(out[8:16]), H.to_int(out[16:24])
+    return (-a if out[24] else a), (-b if out[25] else b), (-d if out[26] else d), bool(out[27])
+
+
+def test_lattice3_invariants(lib):
+    """csrc/lat3.cuh: (b, a, d) with a = b c, d = b u (mod 8r), b odd, all below the 174-bit window budget --
+    for edge and random (c, u); `ok` may only be false if the budget is missed, never true on a wrong vector"""
+    rnd = random.Random(95)
+    N = 8 * R
+    edge = [0, 1, 2, R - 1, (1 << 250) - 1, N // 3 % (1 << 250), (1 << 128), (1 << 170) + 1]
+    cases = [(c, u) for c in edge for u in (0, 1, R - 1, rnd.randrange(R))] + [(rnd.randrange(1 << 250), rnd.randrange(R)) for _ in range(300)]
+    cases += [(c, rnd.randrange(R)) for c in V.hgcd_hostile_challenges(4)]
+    n_ok_random = 0
+    for k, (c, u) in enumerate(cases):
+        a, b, d, ok = _lat3(lib, c, u)
+        if not ok:  # e.g. u = r - 1: every short vector has an even b ((8, ., -8) is in the lattice); the kernel falls back
+            continue
+        n_ok_random += 4 * len(edge) <= k < 4 * len(edge) + 300
+        assert b % 2 == 1 and b != 0
+        assert (a - b * c) % N == 0 and (d - b * u) % N == 0, (hex(c), hex(u))
+        assert max(abs(a), abs(b), abs(d)) < (1 << 174)
+    assert n_ok_random >= 299  # random inputs essentially always meet the budget
+
+
+def test_verify_vargen_short_scalars_equal_full_size(lib):
+    """the 3-table short-scalar form gives the verdict of the reference-shaped full-size form: valid, corrupted,
+    keys / generators / nonce points with torsion components, projective inputs"""
+    import ctypes
+    rnd = random.Random(96)
+    tors = V.torsion_points()
+    fo = ctypes.c_int(1)
+    for trial in range(10):
+        gen = V.mul(o.G, rnd.randrange(1, R))
+        sk, nonce, m = rnd.randrange(R), rnd.randrange(R), rnd.randrange(Q)
+        if trial % 3 == 1:
+            gen = o.pt_add(gen, tors[trial % len(tors)])   # generator outside the prime-order subgroup
+        pk = V.mul(gen, sk)
+        if trial % 3 == 2:
+            pk = o.pt_add(pk, tors[(trial + 3) % len(tors)])
+        c = rnd.randrange(1 << 250)
+        u = rnd.randrange(R)
+        good = o.pt_add(V.mul(gen, u), V.mul(pk, c))      # R that makes u Gen + c PK == R hold
+        for Rp, want in ((good, 1), (o.pt_add(good, o.G), 0), (o.pt_add(good, tors[1]), 0)):
+            z = rnd.randrange(1, Q)
+            for aff, zz in ((1, None), (0, z)):
+                args = (H.ptr(H.pt_mont(pk, zz)), H.ptr(H.pt_mont(gen, zz)), H.ptr(H.limbs(u)), H.ptr(H.pt_mont(Rp, zz)), H.ptr(H.limbs(c)), aff)
+                assert lib.h_verify_vargen_ec(*args, 1, ctypes.byref(fo)) == want and fo.value == 1
+                assert lib.h_verify_vargen_ec(*args, 0, ctypes.byref(fo)) == want
+    # u >= r is rejected by both
+    args = (H.ptr(H.pt_mont(pk)), H.ptr(H.pt_mont(gen)), H.ptr(H.limbs(R)), H.ptr(H.pt_mont(good)), H.ptr(H.limbs(c)), 1)
+    assert lib.h_verify_vargen_ec(*args, 1, ctypes.byref(fo)) == 0 and lib.h_verify_vargen_ec(*args, 0, ctypes.byref(fo)) == 0
