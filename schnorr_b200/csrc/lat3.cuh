@@ -11,14 +11,20 @@
 // determinant N^2 ~ 2^510, so its short vectors have entries ~2^170: a triple-scalar Straus multiplication with 44
 // four-bit windows (172 doublings) replaces the double-scalar one with 64 (252 doublings).
 //
-// The reduction is a greedy (Semaev-style) one, shaped for one tuple per thread with all lanes of a warp in lock-step:
-// every round sorts the three basis vectors by length, takes the middle one modulo the shortest (a Gauss step) and the
-// longest modulo the plane of the other two, with the integer quotients taken from a double-precision Gram matrix of
-// the CURRENT vectors and applied EXACTLY to the 288-bit integer vectors.  Floating-point error can only make a step
-// sub-optimal, never wrong: every basis vector is an integer combination of lattice vectors at all times.  ~70 rounds
-// (measured: 50-87 over random inputs) bring the entries from 2^255 down to <= 2^173; the shortest vector with an odd b
-// is used (the b's of a basis cannot all be even: (1, c, u) is in the lattice).  If none fits the 174-bit window budget
-// `ok` is false and the caller runs the full-size multiplication for that tuple.
+// The reduction is a greedy (Semaev-style) one, shaped for one tuple per thread with all lanes of a warp in lock-step,
+// in two levels like Lehmer's gcd.  INNER rounds work on a double-precision copy F of the three basis vectors and on the
+// 3 x 3 integer transform T accumulated so far (also held in doubles, exactly): sort the vectors by length, take the
+// middle one modulo the shortest (a Gauss step) and the longest modulo the plane of the other two, quotients rounded
+// from the Gram matrix of F.  When T's entries reach 2^20 (F has then lost ~40 of its 53 bits to cancellation) or
+// nothing changes, the OUTER level applies T EXACTLY to the 288-bit integer vectors and refreshes F from them.
+// Floating-point error can only make a step sub-optimal, never wrong: T is unimodular by construction and is applied
+// with exact integer arithmetic, so the three vectors are a basis of the lattice at all times.  ~70 inner rounds in
+// 9-10 outer passes (measured over random inputs: 50-88 / 9-10) bring the entries from 2^255 down to <= 2^173; the
+// shortest basis vector with an odd b is used (the b's of a basis cannot all be even: (1, c, u) is in the lattice).
+// If none fits the 174-bit window budget -- structured inputs such as u = r - 1, where (8, ., -8) is in the lattice
+// and every short vector has an even b -- `ok` is false and the caller runs the full-size multiplication for that
+// tuple.  (A one-level version that updated the 288-bit vectors every round was measured first: its ~1 300
+// instructions per round ate the whole gain, 15.8 -> 16.3 M/s)
 #pragma once
 #include "fq.cuh"
 #include "hgcd.cuh"
@@ -31,7 +37,8 @@ namespace sb200 {
 
 constexpr int LAT3_LIMBS = 9;        // 288-bit two's complement
 constexpr int LAT3_WINDOWS = 44;     // 4-bit windows of the triple-scalar multiplication: magnitudes < 2^174
-constexpr int LAT3_MAX_ROUNDS = 160;
+constexpr int LAT3_MAX_OUTER = 20;    // exact refreshes (measured 9-10)
+constexpr int LAT3_MAX_INNER = 32;    // double-precision rounds between two refreshes
 
 struct lat3_res {
   uint32_t a[8], b[8], d[8];  // magnitudes, < 2^174
@@ -93,24 +100,23 @@ SB_HD void lat3_submul(uint32_t* w, const uint32_t* x, double q) {
   }
 }
 
-SB_HD void lat3_cswap(uint32_t (*A)[LAT3_LIMBS], uint32_t (*B)[LAT3_LIMBS], double* fa, double* fb, double& na, double& nb) {
+SB_HD void lat3_cswap(double* fa, double* fb, double* ta, double* tb, double& na, double& nb) {
   const bool sw = na > nb;
 #pragma unroll
   for (int k = 0; k < 3; k++) {
-#pragma unroll
-    for (int i = 0; i < LAT3_LIMBS; i++) {
-      uint32_t x = A[k][i], y = B[k][i];
-      A[k][i] = sw ? y : x;
-      B[k][i] = sw ? x : y;
-    }
     double x = fa[k], y = fb[k];
     fa[k] = sw ? y : x;
     fb[k] = sw ? x : y;
+    x = ta[k]; y = tb[k];
+    ta[k] = sw ? y : x;
+    tb[k] = sw ? x : y;
   }
   double x = na, y = nb;
   na = sw ? y : x;
   nb = sw ? x : y;
 }
+SB_HD double lat3_dot(const double* a, const double* b) { return lat3_fma(a[0], b[0], lat3_fma(a[1], b[1], a[2] * b[2])); }
+SB_HD double lat3_clamp(double q, double lim) { return q > lim ? lim : (q < -lim ? -lim : q); }
 
 // |v| < 2^174 ?  and |v| as 8 limbs
 SB_HD bool lat3_abs_fits(const uint32_t* v, uint32_t* mag, bool& neg) {
@@ -131,10 +137,12 @@ SB_HD bool lat3_abs_fits(const uint32_t* v, uint32_t* mag, bool& neg) {
 // c < 2^252, u < 2^252 (canonical limbs)
 SB_HD lat3_res lattice3_8r(const uint32_t* c, const uint32_t* u) {
   const uint32_t n8r[8] = SB200_8R_INIT;
-  uint32_t W[3][3][LAT3_LIMBS];  // [vector][coordinate b, a, d][limb]
-#pragma unroll
+  // [vector][coordinate b, a, d][limb]; indexed by loop variables below, so it lives in (L1-resident) local memory:
+  // every lane uses the same index, the accesses are coalesced, and 81 registers stay free
+  uint32_t W[3][3][LAT3_LIMBS];
+#pragma unroll 1
   for (int v = 0; v < 3; v++)
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < 3; k++)
 #pragma unroll
       for (int i = 0; i < LAT3_LIMBS; i++) W[v][k][i] = 0;
@@ -148,59 +156,91 @@ SB_HD lat3_res lattice3_8r(const uint32_t* c, const uint32_t* u) {
   }
   bool done = false;
 #pragma unroll 1
-  for (int round = 0; round < LAT3_MAX_ROUNDS; round++) {
+  for (int outer = 0; outer < LAT3_MAX_OUTER; outer++) {
     if (!SB_WARP_ANY(!done)) break;
-    double F[3][3], nrm[3];
+    double F[3][3], T[3][3], nrm[3];
 #pragma unroll
     for (int v = 0; v < 3; v++) {
 #pragma unroll
-      for (int k = 0; k < 3; k++) F[v][k] = lat3_to_double(W[v][k]);
-      nrm[v] = lat3_fma(F[v][0], F[v][0], lat3_fma(F[v][1], F[v][1], F[v][2] * F[v][2]));
-    }
-    // ascending by length
-    lat3_cswap(W[0], W[1], F[0], F[1], nrm[0], nrm[1]);
-    lat3_cswap(W[1], W[2], F[1], F[2], nrm[1], nrm[2]);
-    lat3_cswap(W[0], W[1], F[0], F[1], nrm[0], nrm[1]);
-    if (done) continue;  // (the swaps above are idempotent on a finished lane)
-    bool changed = false;
-    const double lim = 4503599627370496.0;  // 2^52
-    // Gauss step: the middle vector modulo the shortest
-    double g00 = nrm[0];
-    double g01 = lat3_fma(F[0][0], F[1][0], lat3_fma(F[0][1], F[1][1], F[0][2] * F[1][2]));
-    if (g00 > 0.0) {
-      double q = lat3_rint(g01 / g00);
-      q = q > lim ? lim : (q < -lim ? -lim : q);
-      if (q != 0.0) {
-        changed = true;
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          lat3_submul(W[1][k], W[0][k], q);
-          F[1][k] = lat3_fma(-q, F[0][k], F[1][k]);
-        }
+      for (int k = 0; k < 3; k++) {
+        F[v][k] = lat3_to_double(W[v][k]);
+        T[v][k] = v == k ? 1.0 : 0.0;
       }
     }
-    // the longest vector modulo the plane of the other two (normal equations of the 2 x 2 Gram matrix)
-    g01 = lat3_fma(F[0][0], F[1][0], lat3_fma(F[0][1], F[1][1], F[0][2] * F[1][2]));
-    const double g11 = lat3_fma(F[1][0], F[1][0], lat3_fma(F[1][1], F[1][1], F[1][2] * F[1][2]));
-    const double g02 = lat3_fma(F[0][0], F[2][0], lat3_fma(F[0][1], F[2][1], F[0][2] * F[2][2]));
-    const double g12 = lat3_fma(F[1][0], F[2][0], lat3_fma(F[1][1], F[2][1], F[1][2] * F[2][2]));
-    const double det = lat3_fma(g00, g11, -(g01 * g01));
-    if (det > 0.0) {
-      const double inv = 1.0 / det;
-      double q0 = lat3_rint(lat3_fma(g02, g11, -(g12 * g01)) * inv);
-      double q1 = lat3_rint(lat3_fma(g12, g00, -(g02 * g01)) * inv);
-      q0 = q0 > lim ? lim : (q0 < -lim ? -lim : q0);
-      q1 = q1 > lim ? lim : (q1 < -lim ? -lim : q1);
-      if (q0 != 0.0 || q1 != 0.0) {
-        changed = true;
+    bool any_change = false, stop = done;
+#pragma unroll 1
+    for (int inner = 0; inner < LAT3_MAX_INNER; inner++) {
+      if (!SB_WARP_ANY(!stop)) break;
+      if (stop) continue;
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-          lat3_submul(W[2][k], W[0][k], q0);
-          lat3_submul(W[2][k], W[1][k], q1);
+      for (int v = 0; v < 3; v++) nrm[v] = lat3_dot(F[v], F[v]);
+      lat3_cswap(F[0], F[1], T[0], T[1], nrm[0], nrm[1]);  // ascending by length
+      lat3_cswap(F[1], F[2], T[1], T[2], nrm[1], nrm[2]);
+      lat3_cswap(F[0], F[1], T[0], T[1], nrm[0], nrm[1]);
+      bool changed = false;
+      // quotients are clamped to 2^15 (a clamped quotient is a partial, still valid, step): with |T| < 2^20 before a
+      // round, |T| <= 2^20 (1 + 2 q + q^2) < 2^51 after it, so T stays an exact integer matrix in doubles and its entries
+      // fit lat3_submul's 52-bit multiplier
+      const double qlim = 32768.0, tlim = 1048576.0;
+      const double g00 = nrm[0];
+      if (g00 > 0.0) {  // Gauss step: the middle vector modulo the shortest
+        const double q = lat3_clamp(lat3_rint(lat3_dot(F[0], F[1]) / g00), qlim);
+        if (q != 0.0) {
+          changed = true;
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            F[1][k] = lat3_fma(-q, F[0][k], F[1][k]);
+            T[1][k] = lat3_fma(-q, T[0][k], T[1][k]);
+          }
         }
       }
+      // the longest vector modulo the plane of the other two (normal equations of the 2 x 2 Gram matrix)
+      const double g01 = lat3_dot(F[0], F[1]), g11 = lat3_dot(F[1], F[1]);
+      const double g02 = lat3_dot(F[0], F[2]), g12 = lat3_dot(F[1], F[2]);
+      const double det = lat3_fma(g00, g11, -(g01 * g01));
+      if (det > 0.0) {
+        const double inv = 1.0 / det;
+        const double q0 = lat3_clamp(lat3_rint(lat3_fma(g02, g11, -(g12 * g01)) * inv), qlim);
+        const double q1 = lat3_clamp(lat3_rint(lat3_fma(g12, g00, -(g02 * g01)) * inv), qlim);
+        if (q0 != 0.0 || q1 != 0.0) {
+          changed = true;
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            F[2][k] = lat3_fma(-q1, F[1][k], lat3_fma(-q0, F[0][k], F[2][k]));
+            T[2][k] = lat3_fma(-q1, T[1][k], lat3_fma(-q0, T[0][k], T[2][k]));
+          }
+        }
+      }
+      any_change |= changed;
+      double tmax = 0.0;
+#pragma unroll
+      for (int v = 0; v < 3; v++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) tmax = fmax(tmax, fabs(T[v][k]));
+      stop = !changed || tmax >= tlim;
     }
-    done = !changed;
+    // W <- T W, exactly, one coordinate at a time (lanes that are done carry T = identity)
+    double Tm[3][3];
+#pragma unroll
+    for (int v = 0; v < 3; v++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) Tm[v][k] = done ? (v == k ? 1.0 : 0.0) : T[v][k];
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) {
+      uint32_t nw[3][LAT3_LIMBS];
+#pragma unroll
+      for (int v = 0; v < 3; v++) {
+#pragma unroll
+        for (int i = 0; i < LAT3_LIMBS; i++) nw[v][i] = 0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) lat3_submul(nw[v], W[j][k], -Tm[v][j]);
+      }
+#pragma unroll
+      for (int v = 0; v < 3; v++)
+#pragma unroll
+        for (int i = 0; i < LAT3_LIMBS; i++) W[v][k][i] = nw[v][i];
+    }
+    done |= !any_change;
   }
   // the shortest basis vector with an odd b that fits the window budget
   lat3_res res;

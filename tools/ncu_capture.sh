@@ -6,7 +6,7 @@
 set -u
 op=$1; lg=$2; kre=$3; key=$4; tag=$5; skip=${6:-0}
 rep=/tmp/${op}_${tag}.ncu-rep
-ncu --set full --clock-control none --import-source on -k regex:$kre --launch-skip $skip -c 2 -f -o ${rep%.ncu-rep} python tools/prof_op.py $op $lg 1 > gpurun_out/ncu_${op}_${tag}.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:$kre --launch-skip $skip -c 2 -f -o ${rep%.ncu-rep} python tools/prof_op.py $op $lg 1 > gpurun_out/ncu_${op}_${tag}.log 2>&1
 python tools/ncu_summary.py $rep > gpurun_out/ncu_${op}_${tag}_summary.txt 2>&1
 for id in 1 2; do
   ncu -i $rep --page source --csv --kernel-id :::$id > /tmp/src_${op}_$id.csv 2>/dev/null
