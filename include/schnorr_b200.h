@@ -232,6 +232,9 @@ int sb200_points_check(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t
 /* Building-block probes for the parity tests (same kernels' device functions, one element per thread).
  * op: 0 mul (Montgomery product), 1 add, 2 sub, 3 inverse (b ignored), 4 square, 5 to_mont, 6 from_mont */
 int sb200_dbg_fq(sb200_ctx* ctx, int64_t n, int op, const uint32_t* a, const uint32_t* b, uint32_t* out);
+/* csrc/lat3.cuh on the device: the short vector (b, a, d) of the variable-generator verification for challenges c and
+ * responses u (canonical scalars).  out: 32 words per tuple = |a| (8) | |b| (8) | |d| (8) | aneg, bneg, dneg, ok, 0, 0, 0, 0 */
+int sb200_dbg_lattice3(sb200_ctx* ctx, int64_t n, const uint32_t* c, const uint32_t* u, uint32_t* out);
 /* canonical product a*b mod r */
 int sb200_dbg_fr_mul(sb200_ctx* ctx, int64_t n, const uint32_t* a, const uint32_t* b, uint32_t* out);
 /* Hades252 permutation of n states (5 field elements each, in place); dense != 0 runs the

@@ -121,6 +121,7 @@ def load_library() -> ctypes.CDLL:
         "sb200_sign_vargen_bytes": (ci, [vp, i64, u32] + [u32p] * 5),
         "sb200_dbg_fq": (ci, [vp, i64, ci] + [u32p] * 3),
         "sb200_dbg_fr_mul": (ci, [vp, i64] + [u32p] * 3),
+        "sb200_dbg_lattice3": (ci, [vp, i64] + [u32p] * 3),
         "sb200_dbg_hades": (ci, [vp, i64, ci, u32p]),
         "sb200_dbg_scalar_mul": (ci, [vp, i64, u32, ci] + [u32p] * 3),
     }
@@ -139,7 +140,7 @@ EXPORTED_SYMBOLS = [
     "sb200_verify_vargen", "sb200_sign", "sb200_sign_double", "sb200_sign_vargen", "sb200_keygen",
     "sb200_keygen_double", "sb200_keygen_vargen", "sb200_points_decompress", "sb200_points_compress",
     "sb200_scalars_from_wide", "sb200_fq_to_mont", "sb200_fq_from_mont", "sb200_verify_bytes", "sb200_sign_bytes",
-    "sb200_verify_double_bytes", "sb200_verify_vargen_bytes", "sb200_sign_double_bytes", "sb200_sign_vargen_bytes", "sb200_dbg_fq", "sb200_dbg_fr_mul", "sb200_dbg_hades",
+    "sb200_verify_double_bytes", "sb200_verify_vargen_bytes", "sb200_sign_double_bytes", "sb200_sign_vargen_bytes", "sb200_dbg_fq", "sb200_dbg_fr_mul", "sb200_dbg_lattice3", "sb200_dbg_hades",
     "sb200_dbg_scalar_mul",
 ]
 
@@ -479,6 +480,14 @@ class Engine:
         a, b = _arr(a, 8, n, "a"), _arr(b, 8, n, "b")
         out = aligned_empty((n, 8))
         self._check(self._lib.sb200_dbg_fr_mul(self._h, n, a.ctypes.data, b.ctypes.data, out.ctypes.data), "dbg_fr_mul")
+        return out
+
+    def dbg_lattice3(self, c, u):
+        """(a, b, d, flags) rows of csrc/lat3.cuh run on the device: (n, 32) uint32"""
+        n = np.asarray(c).size // 8
+        c, u = _arr(c, 8, n, "c"), _arr(u, 8, n, "u")
+        out = aligned_empty((n, 32))
+        self._check(self._lib.sb200_dbg_lattice3(self._h, n, c.ctypes.data, u.ctypes.data, out.ctypes.data), "dbg_lattice3")
         return out
 
     def dbg_hades(self, states, dense=False):

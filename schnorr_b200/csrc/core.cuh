@@ -251,7 +251,7 @@ SB_HD bool verify_vargen_ec_fast(const point_in& PK, const point_in& GEN, const 
   uint32_t u[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) u[i] = ok ? u_in[i] : 0u;
-  lat3_res L = lattice3_8r(c_in, u);
+  lat3_res L = lattice3_8r_call(c_in, u);
   fast_ok = L.ok;
   uint32_t kr[24];
 #pragma unroll

@@ -471,7 +471,19 @@ __device__ uint32_t d_fq_mod_lane[8 * 32] = {SB_X32(0x00000001u), SB_X32(0xfffff
 __device__ uint32_t d_fr_mod_lane[8 * 32] = {SB_X32(0xd6f72cb7u), SB_X32(0xd0970e5eu), SB_X32(0xccc81082u), SB_X32(0xa6682093u),
                                             SB_X32(0x01343b00u), SB_X32(0x06673b01u), SB_X32(0x6533afa9u), SB_X32(0x0e7db4eau)};
 #endif
-#if defined(__CUDA_ARCH__)
+#ifndef SB_FQ_MOD_IMM
+#define SB_FQ_MOD_IMM 1  // modulus limbs as immediates (q1 through c_fq_q1); 0 = the per-lane copy in global memory (round 1)
+#endif
+#if defined(__CUDACC__)
+// q1 = 2^32 - 1 must stay a value ptxas does not know: as a literal, every product with it is strength-reduced to
+// IMAD.HI + IMAD.IADD (5 issue cycles instead of 4).  A __constant__ word is opaque (the host could change it) and costs one
+// uniform load per multiplier body.
+__constant__ uint32_t c_fq_q1 = 0xffffffffu;
+#endif
+#if defined(__CUDA_ARCH__) && SB_FQ_MOD_IMM
+#define SB_FQ_MOD(i) ((i) == 1 ? c_fq_q1 : FqP::p(i))
+#define SB_FR_MOD(i) __ldg(&d_fr_mod_lane[(i) * 32 + (threadIdx.x & 31)])
+#elif defined(__CUDA_ARCH__)
 #define SB_FQ_MOD(i) __ldg(&d_fq_mod_lane[(i) * 32 + (threadIdx.x & 31)])
 #define SB_FR_MOD(i) __ldg(&d_fr_mod_lane[(i) * 32 + (threadIdx.x & 31)])
 #else
@@ -578,7 +590,12 @@ SB_HD fq fq_mul_inl(const fq& a, const fq& b) {
     // which ptxas cannot recognise as a negation: when it does, it folds the negation into the multiplies
     // below and emits IMAD + IMAD.HI.U32 pairs for every product with m instead of IMAD.WIDE.U32.X.
     // (Two ALU-pipe instructions; a multiply by q1 would cost the saturated FMA-heavy pipe instead.)
+#if defined(__CUDA_ARCH__) && SB_FQ_MOD_IMM
+    uint32_t m;
+    asm("xor.b32 %0, %1, %2;\n\tadd.u32 %0, %0, 1;" : "=r"(m) : "r"(tprev), "r"(q1));
+#else
     uint32_t m = (tprev ^ q1) + 1u;
+#endif
     blk_red_even_q(X, Y[7], m, q2, q4, q6);
 #if SB_Q1_SHORTCUT
     blk_red_odd_q(Y, m, tprev, q3, q5, q7);

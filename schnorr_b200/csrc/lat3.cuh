@@ -270,4 +270,19 @@ SB_HD lat3_res lattice3_8r(const uint32_t* c, const uint32_t* u) {
   return res;
 }
 
+#ifndef SB_LAT3_OOL
+#define SB_LAT3_OOL 1  // inlined into the three-table curve kernel the reduction was miscompiled (wrong vectors on the GPU, right ones in its own kernel and on the host): tests/test_gpu_robustness.py::test_lattice3_on_the_device, test_vargen_*
+#endif
+#if defined(__CUDA_ARCH__) && SB_LAT3_OOL
+// out of line, arguments and result through local memory: the reduction keeps its own register allocation
+static __device__ __noinline__ void lattice3_8r_ool(const uint32_t* c, const uint32_t* u, lat3_res* r) { *r = lattice3_8r(c, u); }
+SB_HD lat3_res lattice3_8r_call(const uint32_t* c, const uint32_t* u) {
+  lat3_res r;
+  lattice3_8r_ool(c, u, &r);
+  return r;
+}
+#else
+SB_HD lat3_res lattice3_8r_call(const uint32_t* c, const uint32_t* u) { return lattice3_8r(c, u); }
+#endif
+
 }  // namespace sb200

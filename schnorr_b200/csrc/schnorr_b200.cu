@@ -53,7 +53,7 @@ enum Op : int {
   OP_DECOMPRESS, OP_COMPRESS, OP_FROM_WIDE, OP_VERIFY_BYTES, OP_SIGN_BYTES, OP_CHALLENGE, OP_VERIFY_EC,
   OP_VERIFY_DOUBLE_BYTES, OP_VERIFY_VARGEN_BYTES, OP_SIGN_DOUBLE_BYTES, OP_SIGN_VARGEN_BYTES,
   OP_CHALLENGE_DOUBLE, OP_VERIFY_DOUBLE_EC, OP_CHALLENGE_VARGEN, OP_VERIFY_VARGEN_EC, OP_POINTS_CHECK, OP_DBG_VERIFY_EC,
-  OP_DECODE_VERIFY, OP_WITNESS
+  OP_DECODE_VERIFY, OP_WITNESS, OP_DBG_LAT3
 };
 
 struct KArgs {
@@ -332,6 +332,20 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
       default: r = fq_from_mont(x); break;
     }
     if (active) stg8(a.out[0] + i * 8, r.v);
+    return;
+  }
+  if (OP == OP_DBG_LAT3) {  // in: c, u (canonical scalars) -> a | b | d | (aneg, bneg, dneg, ok, 0, 0, 0, 0)
+    uint32_t c[8], u[8];
+    ldg_scalar(a.in[0] + i * 8, c);
+    ldg_scalar(a.in[1] + i * 8, u);
+    lat3_res r = lattice3_8r(c, u);
+    const uint32_t f[8] = {r.aneg, r.bneg, r.dneg, r.ok, 0u, 0u, 0u, 0u};
+    if (active) {
+      stg8(a.out[0] + i * 32, r.a);
+      stg8(a.out[0] + i * 32 + 8, r.b);
+      stg8(a.out[0] + i * 32 + 16, r.d);
+      stg8(a.out[0] + i * 32 + 24, f);
+    }
     return;
   }
   if (OP == OP_DBG_FR_MUL) {
@@ -892,7 +906,7 @@ int launch(sb200_ctx* ctx, Op op, const KArgs& a, cudaStream_t st) {
     CASE(OP_KEYGEN_VARGEN) CASE(OP_DBG_FQ) CASE(OP_DBG_FR_MUL) CASE(OP_DBG_HADES)
     CASE(OP_DBG_SMUL) CASE(OP_DECOMPRESS) CASE(OP_COMPRESS) CASE(OP_FROM_WIDE)
     CASE(OP_SIGN_DOUBLE_BYTES) CASE(OP_SIGN_VARGEN_BYTES)
-    CASE(OP_POINTS_CHECK) CASE(OP_DBG_VERIFY_EC) CASE(OP_WITNESS)
+    CASE(OP_POINTS_CHECK) CASE(OP_DBG_VERIFY_EC) CASE(OP_WITNESS) CASE(OP_DBG_LAT3)
 #undef CASE
     default: return SB200_ERR_ARG;
   }
@@ -1514,6 +1528,12 @@ int sb200_dbg_fq(sb200_ctx* ctx, int64_t n, int op, const uint32_t* a, const uin
   if (!out || op < 0 || op > 6) return SB200_ERR_ARG;
   Desc d; d.op = OP_DBG_FQ; d.flags = 0; d.aux = op; d.nin = 2; d.nout = 1;
   IN(0, a, 8); IN(1, b, b ? 8 : 0); OUT(0, out, 8);
+  return run(ctx, n, d);
+}
+int sb200_dbg_lattice3(sb200_ctx* ctx, int64_t n, const uint32_t* c, const uint32_t* u, uint32_t* out) {
+  if (!out) return SB200_ERR_ARG;
+  Desc d; d.op = OP_DBG_LAT3; d.flags = 0; d.nin = 2; d.nout = 1;
+  IN(0, c, 8); IN(1, u, 8); OUT(0, out, 32);
   return run(ctx, n, d);
 }
 int sb200_dbg_fr_mul(sb200_ctx* ctx, int64_t n, const uint32_t* a, const uint32_t* b, uint32_t* out) {

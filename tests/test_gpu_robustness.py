@@ -280,3 +280,29 @@ def test_vargen_short_scalars_and_their_fallback(engine):
     zs = [rnd.randrange(1, Q) for _ in range(n)]
     ok, _ = engine.verify_vargen(V.points(pk, zs), V.points(gen, zs[::-1]), V.scalars(u), V.points(Rr, zs), V.fqs(msg), affine=False)
     assert ok.tolist() == want
+
+
+@pytest.mark.gpu
+def test_lattice3_on_the_device(engine):
+    """csrc/lat3.cuh as compiled for the GPU (sb200_dbg_lattice3): every reported short vector (b, a, d) satisfies
+    a = b c, d = b u (mod 8r) with b odd and all three below the 174-bit window budget -- edge, structured and random
+    (c, u), several warps, lanes with `ok` = false (u = r - 1) mixed in; random inputs must essentially always fit"""
+    rnd = random.Random(97)
+    N = 8 * R
+    edge = [0, 1, 2, R - 1, (1 << 250) - 1, N // 3 % (1 << 250), 1 << 128, (1 << 170) + 1]
+    cases = [(c, u) for c in edge for u in (0, 1, R - 1, rnd.randrange(R))]
+    n_edge = len(cases)
+    cases += [(rnd.randrange(1 << 250), rnd.randrange(R)) for _ in range(1000)]
+    cases += [(c, rnd.randrange(R)) for c in V.hgcd_hostile_challenges(4)]
+    out = engine.dbg_lattice3(V.scalars([c for c, _ in cases]), V.scalars([u for _, u in cases]))
+    n_ok = 0
+    for k, ((c, u), row) in enumerate(zip(cases, out)):
+        a, b, d = V.to_int(row[:8]), V.to_int(row[8:16]), V.to_int(row[16:24])
+        a, b, d = (-a if row[24] else a), (-b if row[25] else b), (-d if row[26] else d)
+        if not row[27]:
+            continue
+        n_ok += n_edge <= k < n_edge + 1000
+        assert b % 2 == 1, (k, hex(c), hex(u))
+        assert (a - b * c) % N == 0 and (d - b * u) % N == 0, (k, hex(c), hex(u), hex(a), hex(b), hex(d))
+        assert max(abs(a), abs(b), abs(d)) < (1 << 174)
+    assert n_ok >= 998
