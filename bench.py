@@ -176,7 +176,22 @@ def roofline(op_key, n, ms, bytes_io, traffic_key=None):
         if os.path.exists(mp):
             hbm_peak = json.load(open(mp))["hbm_gbs"]
         hbm = bytes_io / (ms * 1e-3) / 1e9
-        return {"bound": "imad", "achieved": achieved, "peak": peak["imad_wide_per_s"] / 1e12, "unit": "T IMAD.WIDE/s",
+        issue = None
+        try:  # issue-slot model: executed warp instructions per tuple from the committed ncu captures
+            ic = json.load(open(os.path.join(ROOT, "profiles", "inst_counts.json")))[op_key]
+            im = json.load(open(os.path.join(ROOT, "profiles", "issue_model.json")))
+            inst = ic["warp_inst_per_tuple"]
+            a_w, b_o = im["cycles_per_wide"], im["cycles_per_other"]
+            smsp_cycles_per_s = im["sm_subpartitions"] * im["sm_hz"]
+            need = (a_w * wide + b_o * (inst - wide)) * n / 32.0  # sub-partition cycles the model asks for this launch
+            issue = {"model": f"{a_w} cycles per IMAD.WIDE + {b_o} per other warp instruction on one SM sub-partition "
+                              "(fit of tools/issue_mix.cu, profiles/issue_mix_r02.json; accuracy about 10 %)",
+                     "warp_inst_per_tuple": inst, "wide_per_tuple": wide, "inst_source": ic["source"],
+                     "predicted_ms": need / smsp_cycles_per_s * 1e3, "measured_ms": ms,
+                     "predicted_over_measured": need / smsp_cycles_per_s * 1e3 / ms}
+        except Exception:
+            issue = None
+        return {"bound": "imad", "issue_model": issue, "achieved": achieved, "peak": peak["imad_wide_per_s"] / 1e12, "unit": "T IMAD.WIDE/s",
                 "frac": achieved / (peak["imad_wide_per_s"] / 1e12),
                 "peak_nominal": peak["nominal_per_s"] / 1e12, "frac_nominal": achieved / (peak["nominal_per_s"] / 1e12),
                 "traffic": ncu_traffic(traffic_key, n) if traffic_key else None,
