@@ -802,9 +802,75 @@ SB_HD fq mont_reduce17(const uint32_t* S) {
   return r;
 }
 
+// S[0..16] = E[0..16] + (O[0..15] << 32)   (O[k] sits at limb position k + 1); the sum fits 17 limbs
+SB_HD void merge_eo17(uint32_t* S, const uint32_t* E, const uint32_t* O) {
+  S[0] = E[0];
+#if defined(__CUDA_ARCH__)
+  asm("add.cc.u32 %0, %16, %32;\n\t"
+      "addc.cc.u32 %1, %17, %33;\n\t"
+      "addc.cc.u32 %2, %18, %34;\n\t"
+      "addc.cc.u32 %3, %19, %35;\n\t"
+      "addc.cc.u32 %4, %20, %36;\n\t"
+      "addc.cc.u32 %5, %21, %37;\n\t"
+      "addc.cc.u32 %6, %22, %38;\n\t"
+      "addc.cc.u32 %7, %23, %39;\n\t"
+      "addc.cc.u32 %8, %24, %40;\n\t"
+      "addc.cc.u32 %9, %25, %41;\n\t"
+      "addc.cc.u32 %10, %26, %42;\n\t"
+      "addc.cc.u32 %11, %27, %43;\n\t"
+      "addc.cc.u32 %12, %28, %44;\n\t"
+      "addc.cc.u32 %13, %29, %45;\n\t"
+      "addc.cc.u32 %14, %30, %46;\n\t"
+      "addc.u32 %15, %31, %47;"
+      : "=r"(S[1]), "=r"(S[2]), "=r"(S[3]), "=r"(S[4]), "=r"(S[5]), "=r"(S[6]), "=r"(S[7]), "=r"(S[8]), "=r"(S[9]), "=r"(S[10]),
+        "=r"(S[11]), "=r"(S[12]), "=r"(S[13]), "=r"(S[14]), "=r"(S[15]), "=r"(S[16])
+      : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]), "r"(E[10]), "r"(E[11]),
+        "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]), "r"(E[16]), "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]),
+        "r"(O[6]), "r"(O[7]), "r"(O[8]), "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]), "r"(O[15]));
+#else
+  uint64_t c = 0;
+  for (int i = 1; i < 17; i++) {
+    c += (uint64_t)E[i] + O[i - 1];
+    S[i] = (uint32_t)c;
+    c >>= 32;
+  }
+#endif
+}
+
+#ifndef SB_DOT5_ROWMAJOR
+#define SB_DOT5_ROWMAJOR 1
+#endif
 // sum_{j<5} c_j * s_j with the constants c_j read through `cst` (5 consecutive field elements)
 SB_HD fq fq_dot5_inl(const uint32_t (*cst)[8], const fq& s0, const fq& s1, const fq& s2, const fq& s3, const fq& s4) {
   SB_COUNT(fq_dot5, 1);
+#if SB_DOT5_ROWMAJOR
+  // All five products accumulate into ONE pair of even- / odd-aligned arrays, limb row by limb row (row i of every product
+  // before row i + 1 of any): the limb that takes a block's carry-out (position i + 8 or i + 9) has then only ever received
+  // carry-outs (at most ten of them), so the plain `addc` at the end of a block cannot overflow -- and the per-product
+  // merge (15 additions) and accumulation (17) of the product-by-product form disappear: 143 instructions less per call.
+  {
+    uint32_t E[18], O[18], S[17];
+#pragma unroll
+    for (int i = 0; i < 18; i++) E[i] = O[i] = 0;
+    const fq* sv[5] = {&s0, &s1, &s2, &s3, &s4};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+#pragma unroll
+      for (int j = 0; j < 5; j++) {
+        const uint32_t a = sv[j]->v[i];
+        if ((i & 1) == 0) {
+          blk_mac4c(E + i, a, cst[j][0], cst[j][2], cst[j][4], cst[j][6]);
+          blk_mac4c(O + i, a, cst[j][1], cst[j][3], cst[j][5], cst[j][7]);
+        } else {
+          blk_mac4c(O + i - 1, a, cst[j][0], cst[j][2], cst[j][4], cst[j][6]);
+          blk_mac4c(E + i + 1, a, cst[j][1], cst[j][3], cst[j][5], cst[j][7]);
+        }
+      }
+    }
+    merge_eo17(S, E, O);
+    return mont_reduce17(S);
+  }
+#endif
   uint32_t S[17], T[16], c[8];
 #pragma unroll
   for (int i = 0; i < 17; i++) S[i] = 0;
