@@ -267,6 +267,9 @@ SB_HD p1p1 pt_dbl(const p1p1& c) {
 #endif
 }
 
+#ifndef SB_TABLE_PREFETCH
+#define SB_TABLE_PREFETCH 0
+#endif
 #ifndef SB_DBL_ROLL
 #define SB_DBL_ROLL 4  // how many of the 4 doublings per window run as a rolled loop
 #endif
@@ -325,6 +328,15 @@ SB_HD p1p1 ed_mul_var2_rolled(const pniels* tab1, const uint32_t* k1_rec, const 
   c = ed_add(p1p1_to_ext(c), vartable_lookup(tab2, recode_digit<4>(k2_rec, nwin - 1)));
 #pragma unroll 1
   for (int i = nwin - 2; i >= 0; i--) {
+#if defined(__CUDA_ARCH__) && SB_TABLE_PREFETCH
+    // tables in global memory (SB_EC_GLOBAL_TABLES): the two entries this window will add are known now -- pull their
+    // 128-byte lines into L1 while the four doublings run
+    {
+      int d1 = recode_digit<4>(k1_rec, i), d2 = recode_digit<4>(k2_rec, i);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(tab1 + (d1 < 0 ? -d1 : d1)));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(tab2 + (d2 < 0 ? -d2 : d2)));
+    }
+#endif
 #pragma unroll 1
     for (int k = 0; k < 4; k++) c = pt_dbl(c);
 #pragma unroll 1
