@@ -33,7 +33,7 @@ def _cubins(blob):
     out = []
     for m in re.finditer(b"\x7fELF\x02\x01\x01", blob):
         off = m.start()
-        if off == 0 or off + 64 > len(blob):
+        if off + 64 > len(blob):
             continue
         e_type, e_machine, _v, _entry, _phoff, shoff, _flags, _ehsize, _phes, _phn, shes, shn, _shstr = struct.unpack_from(
             "<HHIQQQIHHHHHH", blob, off + 16)
