@@ -16,7 +16,7 @@ stall_cols = [(i, h) for i, h in enumerate(hdr) if h.startswith("stall_") and "N
 base = None
 agg = collections.defaultdict(lambda: collections.Counter())
 for r in rows[2:]:
-    if len(r) <= ismp or not r[ia]:
+    if len(r) <= ismp or not r[ia] or r[ia] == "Address":
         continue
     addr = int(r[ia], 16) if r[ia].startswith("0x") else int(r[ia])
     if base is None:
