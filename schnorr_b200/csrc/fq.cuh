@@ -525,10 +525,30 @@ SB_HD fq fq_add(const fq& a, const fq& b) {
   return r;
 }
 
+#ifndef SB_SUB_PREDICATED
+#define SB_SUB_PREDICATED 1
+#endif
 SB_HD fq fq_sub(const fq& a, const fq& b) {
   SB_COUNT(fq_addsub, 1);
   fq r;
   uint32_t borrow = sub8(r.v, a.v, b.v);
+#if defined(__CUDA_ARCH__) && SB_SUB_PREDICATED
+  // add q back under a predicate (8 predicated additions with immediate limbs) instead of masking q first (8 AND + 8 additions)
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.ne.u32 p, %8, 0;\n\t"
+      "@p add.cc.u32 %0, %0, %9;\n\t"
+      "@p addc.cc.u32 %1, %1, %10;\n\t"
+      "@p addc.cc.u32 %2, %2, %11;\n\t"
+      "@p addc.cc.u32 %3, %3, %12;\n\t"
+      "@p addc.cc.u32 %4, %4, %13;\n\t"
+      "@p addc.cc.u32 %5, %5, %14;\n\t"
+      "@p addc.cc.u32 %6, %6, %15;\n\t"
+      "@p addc.u32 %7, %7, %16;\n\t}"
+      : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7])
+      : "r"(borrow), "n"(FqP::p(0)), "n"(FqP::p(1)), "n"(FqP::p(2)), "n"(FqP::p(3)), "n"(FqP::p(4)), "n"(FqP::p(5)), "n"(FqP::p(6)),
+        "n"(FqP::p(7)));
+  return r;
+#endif
   uint32_t t[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) t[i] = FqP::p(i) & borrow;

@@ -82,8 +82,11 @@ SB_HD hgcd_res half_gcd_8r(const uint32_t* c) {
       R0 = (R0 << sh) | (w0 >> (32 - sh));
       R1 = (R1 << sh) | (v0 >> (32 - sh));
     }
-    const uint64_t den = R1 + 1;
-    uint64_t q64 = den ? R0 / den : 0;  // <= floor(r0 / r1)
+    // q <= floor(R0 / (R1 + 1)) <= floor(r0 / r1), from a double-precision quotient scaled down by 2^-50 (the three roundings
+    // -- two conversions and the division -- are each within 2^-53): ~25 instructions instead of the ~90 of a 64-bit integer
+    // division, and the same value on the host build (IEEE division, no contraction possible).  An estimate that is low by one
+    // only costs an extra step.
+    uint64_t q64 = (uint64_t)((double)R0 / ((double)R1 + 1.0) * 0.99999999999999911182158029987);
     if (q64 < 1) q64 = 1;               // r0 >= r1: one subtraction is always possible
     if (q64 > 0x7fffffffull) q64 = 0x7fffffffull;
     const uint32_t q = (uint32_t)q64;
