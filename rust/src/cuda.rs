@@ -130,6 +130,8 @@ extern "C" {
                          u_out: *mut u32, R_out: *mut u32, R_prime_out: *mut u32, c_out: *mut u32) -> c_int;
     fn sb200_sign_vargen(ctx: *mut Sb200Ctx, n: i64, flags: u32, sk: *const u32, generator: *const u32,
                          msg: *const u32, nonce: *const u32, u_out: *mut u32, R_out: *mut u32, c_out: *mut u32) -> c_int;
+    fn sb200_sign_witness(ctx: *mut Sb200Ctx, n: i64, flags: u32, scheme: c_int, sk: *const u32, msg: *const u32,
+                          nonce: *const u32, generator: *const u32, rows_out: *mut u32) -> c_int;
     fn sb200_keygen(ctx: *mut Sb200Ctx, n: i64, flags: u32, sk: *const u32, pk_out: *mut u32) -> c_int;
     fn sb200_keygen_double(ctx: *mut Sb200Ctx, n: i64, flags: u32, sk: *const u32, pk_out: *mut u32,
                            pk_prime_out: *mut u32) -> c_int;
@@ -353,6 +355,33 @@ impl SecretKey {
                        core::ptr::null_mut())
         })?;
         Ok((0..n).map(|i| Signature::new(scalar_at(&u, i), point_at(&r, i))).collect())
+    }
+
+    /// Batch signing that also returns, per signature, the BlsScalar values `Signature::append` (src/signatures.rs:97-103) and
+    /// `gadgets::verify_signature` (src/gadgets.rs:48-68) allocate as witnesses: one row of 11 field elements
+    /// `u, R.u, R.v, PK.u, PK.v, m, c, SA.u, SA.v, SB.u, SB.v` (SA = u G, SB = c PK, SA + SB = R), computed on the device next to
+    /// the signature so that the prover does not repeat the two scalar multiplications on the CPU.
+    pub fn sign_batch_witness<R: RngCore + CryptoRng>(ctx: &CudaCtx, sks: &[SecretKey], rng: &mut R, msgs: &[BlsScalar])
+                                                      -> Result<Vec<(Signature, [BlsScalar; 11])>, CudaError> {
+        let n = sks.len();
+        let (mut sk, mut m, mut nonce) = (Vec32::with_capacity(8 * n), Vec32::with_capacity(8 * n), Vec32::with_capacity(8 * n));
+        for i in 0..n {
+            push_scalar(&mut sk, sks[i].as_ref());
+            push_fq(&mut m, &msgs[i]);
+            push_scalar(&mut nonce, &JubJubScalar::random(&mut *rng));
+        }
+        let mut rows = Vec32::zeroed(8 * 11 * n);
+        ctx.check(unsafe {
+            sb200_sign_witness(ctx.raw, n as i64, 0, 0, sk.as_ptr(), m.as_ptr(), nonce.as_ptr(), core::ptr::null(), rows.as_mut_ptr())
+        })?;
+        Ok((0..n).map(|i| {
+            let mut w = [BlsScalar::zero(); 11];
+            for (k, x) in w.iter_mut().enumerate() { *x = fq_at(&rows, 11 * i + k); }
+            // u as a JubJubScalar: the row holds its embedding in F_q (`BlsScalar::from(JubJubScalar)`), i.e. the same integer
+            let u = JubJubScalar::from_bytes(&w[0].to_bytes()).expect("u < r");
+            let r = JubJubExtended::from(JubJubAffine::from_raw_unchecked(w[1], w[2]));
+            (Signature::new(u, r), w)
+        }).collect())
     }
 
     #[cfg(feature = "double")]
