@@ -230,7 +230,8 @@ int sb200_sign_witness(sb200_ctx* ctx, int64_t n, uint32_t flags, int scheme, co
 int sb200_points_check(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_t* points, uint32_t* ok_bitmap);
 
 /* Building-block probes for the parity tests (same kernels' device functions, one element per thread).
- * op: 0 mul (Montgomery product), 1 add, 2 sub, 3 inverse (b ignored), 4 square, 5 to_mont, 6 from_mont */
+ * op: 0 mul (Montgomery product), 1 add, 2 sub, 3 inverse by Fermat (b ignored), 4 square, 5 to_mont, 6 from_mont,
+ * 7 inverse by the two-level Euclid of csrc/inv.cuh (what the kernels use on public data) */
 int sb200_dbg_fq(sb200_ctx* ctx, int64_t n, int op, const uint32_t* a, const uint32_t* b, uint32_t* out);
 /* csrc/lat3.cuh on the device: the short vector (b, a, d) of the variable-generator verification for challenges c and
  * responses u (canonical scalars).  out: 32 words per tuple = |a| (8) | |b| (8) | |d| (8) | aneg, bneg, dneg, ok, 0, 0, 0, 0 */

@@ -13,6 +13,7 @@
 #include "hades.cuh"
 #include "hgcd.cuh"
 #include "lat3.cuh"
+#include "inv.cuh"
 // The FP64-pipe permutation is a measured experiment that lost; it is compiled only with
 // -DSB_EXPERIMENTAL_FD=1 (its tables are baked by tools/gen_constants.py, not context parameters).
 #ifndef SB_EXPERIMENTAL_FD
@@ -61,7 +62,7 @@ SB_HD void point_to_affine(const point_in& p, fq& u, fq& v) {
     u = p.U;
     v = p.V;
   } else {
-    fq zi = fq_inv(p.Z);
+    fq zi = fq_inv_fast(p.Z);  // public data: the Euclidean inversion (inv.cuh)
     u = fq_mul(p.U, zi);
     v = fq_mul(p.V, zi);
   }
@@ -300,7 +301,7 @@ SB_HD void verify_double_hash_core(const point_in& R, const point_in& Rp, const 
     ru = R.U; rv = R.V; rpu = Rp.U; rpv = Rp.V;
   } else {  // one shared inversion for Z and Z'
     fq zz = fq_mul(R.Z, Rp.Z);
-    fq zi = fq_inv(zz);
+    fq zi = fq_inv_fast(zz);
     fq zi1 = fq_mul(zi, Rp.Z), zi2 = fq_mul(zi, R.Z);
     ru = fq_mul(R.U, zi1); rv = fq_mul(R.V, zi1);
     rpu = fq_mul(Rp.U, zi2); rpv = fq_mul(Rp.V, zi2);
@@ -360,14 +361,17 @@ SB_HD bool verify_double_core(const point_in& PK, const point_in& PKp, const uin
   return verify_double_ec(PK, PKp, u_in, R, Rp, c_out, combG, combGp);
 }
 
-SB_HD void ext_to_affine(const ext& p, fq& u, fq& v) {
-  fq zi = fq_inv(p.Z);
+// oblivious = true keeps Fermat's constant-time a^(q-2) (Z depends on the nonce / secret key when signing)
+SB_HD void ext_to_affine(const ext& p, fq& u, fq& v, bool oblivious = false) {
+  fq zi = oblivious ? fq_inv(p.Z) : fq_inv_fast(p.Z);
   u = fq_mul(p.X, zi);
   v = fq_mul(p.Y, zi);
 }
 
 // Montgomery's trick: z[0..n) <- 1/z[0..n) with ONE inversion and 3(n-1) multiplications (all z[j] != 0:
 // Z coordinates of complete-addition results).  Used to convert several points per thread to affine.
+// FAST: the Euclidean inversion of inv.cuh (data-dependent running time); otherwise Fermat's a^(q-2) (the address-oblivious paths).
+template <bool FAST = true>
 SB_HD void batch_inverse(fq* z, fq* pre, int n) {
   fq acc = z[0];
   pre[0] = fq_one();
@@ -376,7 +380,7 @@ SB_HD void batch_inverse(fq* z, fq* pre, int n) {
     pre[j] = acc;
     acc = fq_mul(acc, z[j]);
   }
-  fq inv = fq_inv(acc);
+  fq inv = FAST ? fq_inv_fast(acc) : fq_inv(acc);
 #pragma unroll 1
   for (int j = n - 1; j > 0; j--) {
     fq zj = z[j];
@@ -440,7 +444,7 @@ SB_HD void sign_core(const uint32_t* sk, const uint32_t* nonce, const fq& m, con
 SB_HD void sign_double_core(const uint32_t* sk, const uint32_t* nonce, const fq& m, const uint32_t* combG,
                             const uint32_t* combGp, uint32_t* u_out, fq& Ru, fq& Rv, fq& Rpu, fq& Rpv, uint32_t* c_out) {
   ext a = fixed_base_mul(combG, nonce), b = fixed_base_mul(combGp, nonce);
-  fq zi = fq_inv(fq_mul(a.Z, b.Z));  // one inversion for both
+  fq zi = fq_inv_fast(fq_mul(a.Z, b.Z));  // one inversion for both
   fq zi1 = fq_mul(zi, b.Z), zi2 = fq_mul(zi, a.Z);
   Ru = fq_mul(a.X, zi1); Rv = fq_mul(a.Y, zi1);
   Rpu = fq_mul(b.X, zi2); Rpv = fq_mul(b.Y, zi2);
@@ -450,7 +454,7 @@ SB_HD void sign_double_core(const uint32_t* sk, const uint32_t* nonce, const fq&
 
 SB_HD void sign_vargen_core(const uint32_t* sk, const point_in& GEN, const uint32_t* nonce, const fq& m, uint32_t* u_out,
                             fq& Ru, fq& Rv, uint32_t* c_out, bool oblivious = false) {
-  ext_to_affine(oblivious ? var_base_mul_oblivious(GEN, nonce) : var_base_mul(GEN, nonce), Ru, Rv);
+  ext_to_affine(oblivious ? var_base_mul_oblivious(GEN, nonce) : var_base_mul(GEN, nonce), Ru, Rv, oblivious);
   chal3(Ru, Rv, m, c_out);
   sign_finish(nonce, c_out, sk, u_out);
 }

@@ -295,7 +295,8 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
     ldg_scalar(a.in[0] + i * 8, sk);
     if (OP == OP_KEYGEN_VARGEN) {
       const point_in g = ldg_point(a.in[1], i, aff);
-      ext_to_affine((a.flags & SB200_SIGN_OBLIVIOUS) ? var_base_mul_oblivious(g, sk) : var_base_mul(g, sk), u, v);
+      ext_to_affine((a.flags & SB200_SIGN_OBLIVIOUS) ? var_base_mul_oblivious(g, sk) : var_base_mul(g, sk), u, v,
+                    (a.flags & SB200_SIGN_OBLIVIOUS) != 0);
     } else {
       ext_to_affine(fixed_base_mul(a.combG, sk), u, v);
     }
@@ -329,6 +330,7 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
       case 3: r = fq_inv(x); break;
       case 4: r = fq_sqr(x); break;
       case 5: r = fq_to_mont(x); break;
+      case 7: r = fq_inv_fast(x); break;
       default: r = fq_from_mont(x); break;
     }
     if (active) stg8(a.out[0] + i * 8, r.v);
@@ -602,6 +604,73 @@ __host__ __device__ constexpr int fixed_k(int op) { return (op == OP_KEYGEN || o
 // CT = true (SB200_SIGN_OBLIVIOUS): the scalar multiples come from 4-bit combs staged in shared memory and read
 // by masked scan (ed.cuh), so no address depends on a nonce or key -- the "branch-free fixed-base comb tables staged in
 // shared memory" form; 64 additions per multiple instead of 16 (measured: DESIGN.md 4.2).
+#ifndef SB_CTA_INVERSE
+#define SB_CTA_INVERSE 0  // measured with Fermat's inversion: sign 65.4 -> 67.2 M/s, keygen 411 -> 462 M/s, sign_double -0.8 % (the lone inverting warp per sub-partition runs at ~57 % efficiency); superseded by the Euclidean inversion (inv.cuh), which leaves nothing worth sharing
+#endif
+// One field inversion per CTA instead of one per warp.  In SIMT terms the 32 lanes of a warp already share the instruction
+// stream of "their" inversion; what can still be shared is the stream itself, between the four warps of a CTA: every thread
+// leaves the product it wants inverted in shared memory, ONE warp (rotating with the CTA index, so that the four SM
+// sub-partitions take turns) multiplies the four values of its lane position together, inverts once (78 multiplications +
+// 256 squarings) and unfolds the four inverses with six more multiplications, while the other three warps wait at the
+// barrier without issuing anything.  Saves 3 of 4 inversions per CTA: 6.5 % of a signature's issue time, 20 % of a key's.
+__device__ __forceinline__ fq cta_shared_inverse(const fq& acc) {
+#if SB_CTA_INVERSE
+  static_assert(TPB == 128, "four warps per CTA");
+  __shared__ uint32_t sh[8][TPB];  // limb-major: conflict-free
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lead = blockIdx.x & 3;
+#pragma unroll
+  for (int k = 0; k < 8; k++) sh[k][threadIdx.x] = acc.v[k];
+  __syncthreads();
+  if (warp == lead) {  // warp-uniform
+    fq v[4];
+#pragma unroll
+    for (int w = 0; w < 4; w++)
+#pragma unroll
+      for (int k = 0; k < 8; k++) v[w].v[k] = sh[k][w * 32 + lane];
+    const fq p1 = fq_mul(v[0], v[1]), p2 = fq_mul(p1, v[2]);
+    fq t = fq_inv(fq_mul(p2, v[3]));
+    const fq i3 = fq_mul(t, p2);
+    t = fq_mul(t, v[3]);
+    const fq i2 = fq_mul(t, p1);
+    t = fq_mul(t, v[2]);
+    const fq i1 = fq_mul(t, v[0]), i0 = fq_mul(t, v[1]);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      sh[k][lane] = i0.v[k];
+      sh[k][32 + lane] = i1.v[k];
+      sh[k][64 + lane] = i2.v[k];
+      sh[k][96 + lane] = i3.v[k];
+    }
+  }
+  __syncthreads();
+  fq r;
+#pragma unroll
+  for (int k = 0; k < 8; k++) r.v[k] = sh[k][threadIdx.x];
+  return r;
+#else
+  return fq_inv(acc);
+#endif
+}
+// z[0..n) <- 1 / z[0..n): Montgomery's trick inside the thread (core.cuh batch_inverse) around the CTA-shared inversion
+template <bool FAST>
+__device__ __forceinline__ void batch_inverse_cta(fq* z, fq* pre, int n) {
+  fq acc = z[0];
+  pre[0] = fq_one();
+#pragma unroll 1
+  for (int j = 1; j < n; j++) {
+    pre[j] = acc;
+    acc = fq_mul(acc, z[j]);
+  }
+  fq inv = SB_CTA_INVERSE ? cta_shared_inverse(acc) : (FAST ? fq_inv_fast(acc) : fq_inv(acc));
+#pragma unroll 1
+  for (int j = n - 1; j > 0; j--) {
+    fq zj = z[j];
+    z[j] = fq_mul(inv, pre[j]);
+    inv = fq_mul(inv, zj);
+  }
+  z[0] = inv;
+}
+
 template <int OP, bool CT = false>
 __global__ void __launch_bounds__(TPB, CT ? 2 : 4) k_fixed_batch(const KArgs a) {
   constexpr int SIGN_K = fixed_k(OP);
@@ -639,7 +708,7 @@ __global__ void __launch_bounds__(TPB, CT ? 2 : 4) k_fixed_batch(const KArgs a) 
       X[SIGN_K + j] = q.X; Y[SIGN_K + j] = q.Y; Z[SIGN_K + j] = q.Z;
     }
   }
-  batch_inverse(Z, pre, NP);
+  batch_inverse_cta<!CT>(Z, pre, NP);  // the address-oblivious signer keeps Fermat's constant-time inversion
 #pragma unroll 1
   for (int j = 0; j < SIGN_K; j++) {
     int64_t i = base + (int64_t)j * TPB;
@@ -1525,7 +1594,7 @@ int sb200_dbg_verify_ec(sb200_ctx* ctx, int64_t n, uint32_t flags, const uint32_
   return run(ctx, n, d);
 }
 int sb200_dbg_fq(sb200_ctx* ctx, int64_t n, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
-  if (!out || op < 0 || op > 6) return SB200_ERR_ARG;
+  if (!out || op < 0 || op > 7) return SB200_ERR_ARG;
   Desc d; d.op = OP_DBG_FQ; d.flags = 0; d.aux = op; d.nin = 2; d.nout = 1;
   IN(0, a, 8); IN(1, b, b ? 8 : 0); OUT(0, out, 8);
   return run(ctx, n, d);

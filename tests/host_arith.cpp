@@ -126,6 +126,8 @@ void h_fixed_mul_oblivious(const uint32_t* comb4, const uint32_t* k, uint32_t* u
 void h_var_mul_oblivious(const uint32_t* p, int affine, const uint32_t* k, uint32_t* uv) {
   fq a, b; ext_to_affine(var_base_mul_oblivious(P(p, affine), k), a, b); S(uv, a); S(uv + 8, b);
 }
+void h_fq_inv_fast(const uint32_t* a, uint32_t* r) { S(r, fq_inv_fast(L(a))); }
+void h_fq_inv_fermat(const uint32_t* a, uint32_t* r) { S(r, fq_inv(L(a))); }
 // 3-dimensional short vector for the variable-generator verification: out = a[8] | b[8] | d[8] | aneg bneg dneg ok
 void h_lattice3(const uint32_t* c, const uint32_t* u, uint32_t* out) {
   lat3_res r = lattice3_8r(c, u);

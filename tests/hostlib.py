@@ -14,7 +14,7 @@ def build():
     so = os.path.join(ROOT, "build", "host_arith.so")
     src = os.path.join(ROOT, "tests", "host_arith.cpp")
     hdrs = [os.path.join(ROOT, "schnorr_b200", "csrc", f) for f in (
-        "fq.cuh", "experimental/fd.cuh", "ed.cuh", "hades.cuh", "experimental/hades_fd.cuh", "core.cuh", "wire.cuh", "hgcd.cuh",
+        "fq.cuh", "experimental/fd.cuh", "ed.cuh", "hades.cuh", "experimental/hades_fd.cuh", "core.cuh", "wire.cuh", "hgcd.cuh", "lat3.cuh", "inv.cuh",
         "params_host.cuh", "constants_gen.cuh", "experimental/constants_fd_gen.cuh")]
     newest = max(os.path.getmtime(p) for p in [src] + hdrs)
     if not os.path.exists(so) or os.path.getmtime(so) < newest:

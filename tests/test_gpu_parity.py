@@ -40,6 +40,20 @@ def test_fq_inv(engine):
     assert V.ints_out(engine.dbg_fq(3, V.fqs([0]))) == [0]
 
 
+def test_fq_inv_euclid(engine):
+    """csrc/inv.cuh on the device (op 7): the two-level Euclidean inversion against the big-int inverse -- random values, edge
+    values, and values whose Montgomery form is a SMALL integer (first quotient ~2^220: those lanes give up and are inverted by
+    Fermat after a warp vote) mixed into the same warps; 0 -> 0"""
+    rnd = random.Random(14)
+    rinv = pow(V.RADIX, -1, Q)
+    small = [k * rinv % Q for k in (1, 2, 3, 0xFFFFFFFF, 1 << 32, (1 << 64) + 5, (1 << 100) - 1, (1 << 213) + 12345)]
+    xs = [x for x in edge_fq() if x] + small + [rnd.randrange(1, Q) for _ in range(500)]
+    xs += [rnd.choice(small) if i % 5 == 0 else rnd.randrange(1, Q) for i in range(300)]
+    got = V.ints_out(engine.dbg_fq(7, V.fqs(xs)))
+    assert got == [pow(x, -1, Q) * V.RADIX % Q for x in xs]
+    assert V.ints_out(engine.dbg_fq(7, V.fqs([0, 5, 0]))) == [0, pow(5, -1, Q) * V.RADIX % Q, 0]
+
+
 def test_fr_mul(engine):
     rnd = random.Random(13)
     xs = [0, 1, R - 1, (1 << 250) - 1, 1 << 251] + [rnd.randrange(R) for _ in range(300)]

@@ -448,3 +448,21 @@ def test_verify_vargen_short_scalars_equal_full_size(lib):
     # u >= r is rejected by both
     args = (H.ptr(H.pt_mont(pk)), H.ptr(H.pt_mont(gen)), H.ptr(H.limbs(R)), H.ptr(H.pt_mont(good)), H.ptr(H.limbs(c)), 1)
     assert lib.h_verify_vargen_ec(*args, 1, ctypes.byref(fo)) == 0 and lib.h_verify_vargen_ec(*args, 0, ctypes.byref(fo)) == 0
+
+
+def test_euclidean_inversion_equals_fermat(lib):
+    """csrc/inv.cuh: the two-level Euclidean inversion returns exactly a^-1 (Montgomery in, Montgomery out) -- against the big-int
+    inverse and against the Fermat form it replaces -- for edge values (0 -> 0, 1, q - 1, 2, 2^255 mod q, values whose Euclid has
+    huge / tiny quotients) and random ones"""
+    rnd = random.Random(98)
+    vals = [0, 1, 2, 3, Q - 1, Q - 2, (Q - 1) // 2, (Q + 1) // 2, 1 << 128, (1 << 128) - 1, (1 << 254) % Q, pow(2, 256, Q), pow(3, Q - 2, Q),
+            Q // 3, Q // 65537, (Q // 3) * 2 + 1, 0xFFFFFFFF, 1 << 32, (1 << 200) + 1]
+    vals += [rnd.randrange(Q) for _ in range(400)]
+    vals += [rnd.randrange(1 << rnd.randrange(1, 255)) for _ in range(100)]
+    for a in vals:
+        out, ref = np.zeros(8, np.uint32), np.zeros(8, np.uint32)
+        lib.h_fq_inv_fast(H.ptr(H.mont(a)), H.ptr(out))
+        lib.h_fq_inv_fermat(H.ptr(H.mont(a)), H.ptr(ref))
+        want = pow(a, Q - 2, Q)
+        assert H.unmont(out) == want, hex(a)
+        assert (out == ref).all()
