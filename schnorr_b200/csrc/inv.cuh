@@ -79,8 +79,9 @@ SB_HD fq fq_inv_euclid(const fq& A, bool& ok) {
       const double tmax = fmax(fmax(fabs(T[0][0]), fabs(T[0][1])), fmax(fabs(T[1][0]), fabs(T[1][1])));
       stop = !changed || tmax >= 1048576.0;
     }
-    // (r, t) rows <- T (r, t) rows, exactly; finished lanes carry the identity
-#pragma unroll 1
+    // (r, t) rows <- T (r, t) rows, exactly; finished lanes carry the identity.  Fully unrolled: W is indexed statically
+    // everywhere and stays in registers (the function is out of line with its own allocation).
+#pragma unroll
     for (int k = 0; k < 2; k++) {
       uint32_t nw[2][LAT3_LIMBS];
 #pragma unroll
