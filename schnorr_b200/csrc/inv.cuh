@@ -15,6 +15,9 @@
 
 namespace sb200 {
 
+#ifndef SB_INV_UNROLL
+#define SB_INV_UNROLL 1
+#endif
 constexpr int INV_MAX_OUTER = 24;   // measured 9-14 on random input
 constexpr int INV_MAX_INNER = 32;
 
@@ -81,7 +84,11 @@ SB_HD fq fq_inv_euclid(const fq& A, bool& ok) {
     }
     // (r, t) rows <- T (r, t) rows, exactly; finished lanes carry the identity.  Fully unrolled: W is indexed statically
     // everywhere and stays in registers (the function is out of line with its own allocation).
+#if SB_INV_UNROLL
 #pragma unroll
+#else
+#pragma unroll 1
+#endif
     for (int k = 0; k < 2; k++) {
       uint32_t nw[2][LAT3_LIMBS];
 #pragma unroll
