@@ -152,9 +152,13 @@ SB_HD half_scalars half_scalars_prepare(const uint32_t* u, const uint32_t* c_in)
 // `store` = 18 table entries of this thread in caller-provided memory, or nullptr for a local array.  Local memory is
 // word-interleaved across a warp, so a lookup with a per-lane index pulls a different 32-byte sector for every word of
 // every lane; a thread-major region in global memory serves each lookup with four full sectors instead.
+#ifndef SB_TABLE_STAGE
+#define SB_TABLE_STAGE 1  // with SB_EC_GLOBAL_TABLES: stage each window's two entries into shared memory by cp.async (ed.cuh)
+#endif
 template <bool EXT = false>
 SB_HD bool verify_ec_half(const point_in& PK, const point_in& R, const half_scalars& hs, const uint32_t* comb,
-                          pniels* store = nullptr) {
+                          pniels* store = nullptr, uint4* stage = nullptr) {
+  (void)stage;
   pniels local_tabs[EXT ? 1 : 18];
   pniels* tabs0 = EXT ? store : local_tabs;  // [0..9): multiples of -sign(b) R (|b| of them make -b R)
   pniels* tabs1 = tabs0 + 9;                 // [9..18): multiples of PK
@@ -163,21 +167,25 @@ SB_HD bool verify_ec_half(const point_in& PK, const point_in& R, const half_scal
 #pragma unroll 1
     for (int t = 0; t < 2; t++) vartable_build(t ? tabs1 : tabs0, point_to_ext(t ? PK : nR));  // one copy of the table code
   }
+#if defined(__CUDA_ARCH__) && SB_TABLE_STAGE
+  p1p1 cp = EXT ? ed_mul_var2_staged(tabs0, hs.h.b, tabs1, hs.h.a, 34, stage) : ed_mul_var2_rolled(tabs0, hs.h.b, tabs1, hs.h.a, 34);
+#else
   p1p1 cp = ed_mul_var2_rolled(tabs0, hs.h.b, tabs1, hs.h.a, 34);
+#endif
   cp = ed_comb_add(p1p1_to_ext(cp), comb, hs.w);
   // identity <=> X = E F = 0 and Y = G H = Z = F G with F, G != 0 (complete addition) <=> E = 0 and H = F
   return fq_is_zero(cp.E) & fq_eq(cp.H, cp.F);
 }
 template <bool EXT = false>
 SB_HD bool verify_ec_core_fast(const point_in& PK, const uint32_t* u_in, const point_in& R, const uint32_t* c_in,
-                               const uint32_t* combG, bool& fast_ok, pniels* store = nullptr) {
+                               const uint32_t* combG, bool& fast_ok, pniels* store = nullptr, uint4* stage = nullptr) {
   bool ok = scalar_lt_r(u_in);
   uint32_t u[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) u[i] = ok ? u_in[i] : 0u;
   half_scalars hs = half_scalars_prepare(u, c_in);
   fast_ok = hs.h.ok;
-  return ok & verify_ec_half<EXT>(PK, R, hs, combG, store);
+  return ok & verify_ec_half<EXT>(PK, R, hs, combG, store, stage);
 }
 
 #ifndef SB_VERIFY_HGCD
@@ -186,10 +194,10 @@ SB_HD bool verify_ec_core_fast(const point_in& PK, const uint32_t* u_in, const p
 // c PK + u G == R, by the half-size form where it applies
 template <bool EXT = false>
 SB_HD bool verify_ec(const point_in& PK, const uint32_t* u_in, const point_in& R, const uint32_t* c_in, const uint32_t* combG,
-                     pniels* store = nullptr) {
+                     pniels* store = nullptr, uint4* stage = nullptr) {
 #if SB_VERIFY_HGCD
   bool fast_ok;
-  bool ok = verify_ec_core_fast<EXT>(PK, u_in, R, c_in, combG, fast_ok, store);
+  bool ok = verify_ec_core_fast<EXT>(PK, u_in, R, c_in, combG, fast_ok, store, stage);
   if (SB_WARP_ANY(!fast_ok)) {
     bool slow = verify_ec_core(PK, u_in, R, c_in, combG);
     ok = fast_ok ? ok : slow;

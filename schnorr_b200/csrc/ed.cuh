@@ -350,6 +350,53 @@ SB_HD p1p1 ed_mul_var2_rolled(const pniels* tab1, const uint32_t* k1_rec, const 
   return c;
 }
 
+#if defined(__CUDACC__)
+// The same loop for window tables that live in GLOBAL memory (thread-major, one contiguous 128-byte entry per lookup:
+// SB_EC_GLOBAL_TABLES), with the two entries of a window staged into shared memory by cp.async while its four doublings
+// run: the lookups become conflict-free LDS.128 of data that is already on chip, and no register is held for them.
+// `stage` = this CTA's 2 x 8 x blockDim.x uint4 (each thread only ever touches its own slots: no barrier needed).
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ p1p1 ed_mul_var2_staged(const pniels* tab1, const uint32_t* k1_rec, const pniels* tab2, const uint32_t* k2_rec,
+                                                   int nwin, uint4* stage) {
+  const int nthr = blockDim.x, tid = threadIdx.x;
+  p1p1 c = ed_add(ext_identity(), vartable_lookup(tab1, recode_digit<4>(k1_rec, nwin - 1)));
+  c = ed_add(p1p1_to_ext(c), vartable_lookup(tab2, recode_digit<4>(k2_rec, nwin - 1)));
+#pragma unroll 1
+  for (int i = nwin - 2; i >= 0; i--) {
+    const int d1 = recode_digit<4>(k1_rec, i), d2 = recode_digit<4>(k2_rec, i);
+    {
+      const uint4* s1 = reinterpret_cast<const uint4*>(tab1 + (d1 < 0 ? -d1 : d1));
+      const uint4* s2 = reinterpret_cast<const uint4*>(tab2 + (d2 < 0 ? -d2 : d2));
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        cp_async16(stage + k * nthr + tid, s1 + k);
+        cp_async16(stage + (8 + k) * nthr + tid, s2 + k);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) c = pt_dbl(c);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll 1
+    for (int t = 0; t < 2; t++) {
+      const uint4* sp = stage + (8 * t) * nthr + tid;
+      pniels q;
+      uint4 v0 = sp[0], v1 = sp[nthr], v2 = sp[2 * nthr], v3 = sp[3 * nthr], v4 = sp[4 * nthr], v5 = sp[5 * nthr], v6 = sp[6 * nthr],
+            v7 = sp[7 * nthr];
+      q.YpX = {{v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w}};
+      q.YmX = {{v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w}};
+      q.Z = {{v4.x, v4.y, v4.z, v4.w, v5.x, v5.y, v5.z, v5.w}};
+      q.T2d = {{v6.x, v6.y, v6.z, v6.w, v7.x, v7.y, v7.z, v7.w}};
+      ext e = p1p1_to_ext(c);
+      c = ed_add(e, pniels_cneg(q, (t ? d2 : d1) < 0));
+    }
+  }
+  return c;
+}
+#endif
+
 // Straus over THREE variable points (the variable-generator verification with short scalars, lat3.cuh):
 // tabs = 27 entries (three 9-entry tables back to back), kr = three offset-recoded scalars (8 limbs each).
 // One copy of the conversion + lookup + addition sequence, as in ed_mul_var2_rolled.
