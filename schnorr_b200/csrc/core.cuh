@@ -254,8 +254,10 @@ SB_HD bool verify_vargen_ec(const point_in& PK, const point_in& GEN, const uint3
 #ifndef SB_VARGEN_LAT3
 #define SB_VARGEN_LAT3 1
 #endif
+template <bool EXT = false>
 SB_HD bool verify_vargen_ec_fast(const point_in& PK, const point_in& GEN, const uint32_t* u_in, const point_in& R,
-                                 const uint32_t* c_in, bool& fast_ok) {
+                                 const uint32_t* c_in, bool& fast_ok, pniels* store = nullptr, uint4* stage = nullptr) {
+  (void)stage;
   bool ok = scalar_lt_r(u_in);
   uint32_t u[8];
 #pragma unroll
@@ -269,7 +271,8 @@ SB_HD bool verify_vargen_ec_fast(const point_in& PK, const point_in& GEN, const 
     kr[8 + i] = L.a[i];
     kr[16 + i] = L.b[i];
   }
-  pniels tabs[27];  // multiples of sgn(d) Gen, sgn(a) PK, -sgn(b) R
+  pniels local_tabs[EXT ? 1 : 27];  // multiples of sgn(d) Gen, sgn(a) PK, -sgn(b) R (EXT: in the caller's global scratch)
+  pniels* tabs = EXT ? store : local_tabs;
 #pragma unroll 1
   for (int t = 0; t < 3; t++) {
     const point_in& P = t == 0 ? GEN : t == 1 ? PK : R;
@@ -277,16 +280,21 @@ SB_HD bool verify_vargen_ec_fast(const point_in& PK, const point_in& GEN, const 
     vartable_build(tabs + 9 * t, point_to_ext(neg ? point_neg(P) : P));
     recode_offset<4>(kr + 8 * t);
   }
+#if defined(__CUDA_ARCH__) && SB_TABLE_STAGE
+  p1p1 cp = EXT ? ed_mul_var3_staged(tabs, kr, LAT3_WINDOWS, stage) : ed_mul_var3_rolled(tabs, kr, LAT3_WINDOWS);
+#else
   p1p1 cp = ed_mul_var3_rolled(tabs, kr, LAT3_WINDOWS);
+#endif
   // identity <=> E = 0 and H = F (see verify_ec_half)
   return ok & fq_is_zero(cp.E) & fq_eq(cp.H, cp.F);
 }
 // u Gen + c PK == R, by the short-scalar form where it applies
+template <bool EXT = false>
 SB_HD bool verify_vargen_ec_auto(const point_in& PK, const point_in& GEN, const uint32_t* u_in, const point_in& R,
-                                 const uint32_t* c_in) {
+                                 const uint32_t* c_in, pniels* store = nullptr, uint4* stage = nullptr) {
 #if SB_VARGEN_LAT3
   bool fast_ok;
-  bool ok = verify_vargen_ec_fast(PK, GEN, u_in, R, c_in, fast_ok);
+  bool ok = verify_vargen_ec_fast<EXT>(PK, GEN, u_in, R, c_in, fast_ok, store, stage);
   if (SB_WARP_ANY(!fast_ok)) {
     bool slow = verify_vargen_ec(PK, GEN, u_in, R, c_in);
     ok = fast_ok ? ok : slow;
@@ -343,8 +351,10 @@ SB_HD bool verify_double_ec_core(const point_in& PK, const point_in& PKp, const 
   return ok;
 }
 // ... with half-size scalars where they fit (one short vector serves both equations: same c, same u)
+template <bool EXT = false>
 SB_HD bool verify_double_ec(const point_in& PK, const point_in& PKp, const uint32_t* u_in, const point_in& R, const point_in& Rp,
-                            const uint32_t* c_in, const uint32_t* combG, const uint32_t* combGp) {
+                            const uint32_t* c_in, const uint32_t* combG, const uint32_t* combGp, pniels* store = nullptr,
+                            uint4* stage = nullptr) {
 #if SB_VERIFY_HGCD
   bool ok = scalar_lt_r(u_in);
   uint32_t u[8];
@@ -352,7 +362,7 @@ SB_HD bool verify_double_ec(const point_in& PK, const point_in& PKp, const uint3
   for (int i = 0; i < 8; i++) u[i] = ok ? u_in[i] : 0u;
   half_scalars hs = half_scalars_prepare(u, c_in);
 #pragma unroll 1
-  for (int k = 0; k < 2; k++) ok &= verify_ec_half(k ? PKp : PK, k ? Rp : R, hs, k ? combGp : combG);
+  for (int k = 0; k < 2; k++) ok &= verify_ec_half<EXT>(k ? PKp : PK, k ? Rp : R, hs, k ? combGp : combG, store, stage);
   if (SB_WARP_ANY(!hs.h.ok)) {
     bool slow = verify_double_ec_core(PK, PKp, u_in, R, Rp, c_in, combG, combGp);
     ok = hs.h.ok ? ok : slow;

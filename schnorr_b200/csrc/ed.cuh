@@ -395,6 +395,8 @@ __device__ __forceinline__ p1p1 ed_mul_var2_staged(const pniels* tab1, const uin
   }
   return c;
 }
+// three tables (lat3.cuh): 24 staged uint4 per thread and window
+__device__ __forceinline__ p1p1 ed_mul_var3_staged(const pniels* tabs, const uint32_t* kr, int nwin, uint4* stage);
 #endif
 
 // Straus over THREE variable points (the variable-generator verification with short scalars, lat3.cuh):
@@ -416,6 +418,45 @@ SB_HD p1p1 ed_mul_var3_rolled(const pniels* tabs, const uint32_t* kr, int nwin) 
   }
   return c;
 }
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ p1p1 ed_mul_var3_staged(const pniels* tabs, const uint32_t* kr, int nwin, uint4* stage) {
+  const int nthr = blockDim.x, tid = threadIdx.x;
+  p1p1 c = ed_add(ext_identity(), vartable_lookup(tabs, recode_digit<4>(kr, nwin - 1)));
+#pragma unroll 1
+  for (int t = 1; t < 3; t++) c = ed_add(p1p1_to_ext(c), vartable_lookup(tabs + 9 * t, recode_digit<4>(kr + 8 * t, nwin - 1)));
+#pragma unroll 1
+  for (int i = nwin - 2; i >= 0; i--) {
+    int d[3];
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+      d[t] = recode_digit<4>(kr + 8 * t, i);
+      const uint4* sp = reinterpret_cast<const uint4*>(tabs + 9 * t + (d[t] < 0 ? -d[t] : d[t]));
+#pragma unroll
+      for (int k = 0; k < 8; k++) cp_async16(stage + (8 * t + k) * nthr + tid, sp + k);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) c = pt_dbl(c);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const unsigned negs = (d[0] < 0 ? 1u : 0u) | (d[1] < 0 ? 2u : 0u) | (d[2] < 0 ? 4u : 0u);
+#pragma unroll 1
+    for (int t = 0; t < 3; t++) {
+      const uint4* sp = stage + (8 * t) * nthr + tid;
+      pniels q;
+      uint4 v0 = sp[0], v1 = sp[nthr], v2 = sp[2 * nthr], v3 = sp[3 * nthr], v4 = sp[4 * nthr], v5 = sp[5 * nthr], v6 = sp[6 * nthr],
+            v7 = sp[7 * nthr];
+      q.YpX = {{v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w}};
+      q.YmX = {{v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w}};
+      q.Z = {{v4.x, v4.y, v4.z, v4.w, v5.x, v5.y, v5.z, v5.w}};
+      q.T2d = {{v6.x, v6.y, v6.z, v6.w, v7.x, v7.y, v7.z, v7.w}};
+      ext e = p1p1_to_ext(c);
+      c = ed_add(e, pniels_cneg(q, ((negs >> t) & 1u) != 0));
+    }
+  }
+  return c;
+}
+#endif
 
 // ------------------------------------------------------------------------------------------
 // fixed-base comb.  Table layout: window j, entry e (0..2^(W-1)) = e * 2^(W*j) * B in affine Niels form,

@@ -78,7 +78,7 @@ struct KArgs {
   const uint32_t* comb4Gp;
   struct WsState* ws;
   int nsm;
-  pniels* ec_scratch;  // window tables of k_verify_ec_p: EC_P_CTAS * nsm * TPB threads x 18 entries (per stream)
+  pniels* ec_scratch;  // window tables of k_curve_p: 4 * nsm * TPB threads x EC_P_ENTRIES entries (per stream)
   uint8_t* scratch;          // device-only rows between the kernels of one call (challenges, decoded byte-level inputs)
   const uint32_t* inv_mask;  // curve kernels: verdict word &= ~inv_mask word (tuples whose from_bytes failed)
   uint32_t* dec[MAX_IN];     // decode kernel: where the decoded arrays of the byte-level verify calls go
@@ -203,6 +203,9 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
   if (OP == OP_CHALLENGE_VARGEN) {  // in: -, -, -, R, m -> out0: c
     verify_hash_core(ldg_point(a.in[3], i, aff), ldg_fq(a.in[4] + i * 8), c);
     if (active) stg8(a.out[0] + i * 8, c);
+#if SB_EC_GLOBAL_TABLES
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.ws->tile = 0;  // the persistent curve kernel's work counter
+#endif
     return;
   }
   if (OP == OP_VERIFY_VARGEN_EC) {  // in: pk, gen, u, R, - ; out0 (as input): c -> bitmap
@@ -222,6 +225,9 @@ __global__ void __launch_bounds__(TPB, min_ctas(OP)) k_run(const KArgs a) {
   if (OP == OP_CHALLENGE_DOUBLE) {  // in: -, -, -, R, R', m -> out0: c
     verify_double_hash_core(ldg_point(a.in[3], i, aff), ldg_point(a.in[4], i, aff), ldg_fq(a.in[5] + i * 8), c);
     if (active) stg8(a.out[0] + i * 8, c);
+#if SB_EC_GLOBAL_TABLES
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.ws->tile = 0;  // the persistent curve kernel's work counter
+#endif
     return;
   }
   if (OP == OP_VERIFY_DOUBLE_EC) {  // in: pk, pk', u, R, R', - ; out0 (as input): c -> bitmap
@@ -576,12 +582,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_verify_ws(const KArgs a) {
 // Curve half of the single-key verification as a persistent kernel whose window tables live in a thread-major global
 // scratch region (18 entries x 128 B per resident thread) instead of local memory: see verify_ec_half.
 #if SB_EC_GLOBAL_TABLES
-constexpr int EC_P_CTAS = 4;
-__global__ void __launch_bounds__(TPB, EC_P_CTAS) k_verify_ec_p(const KArgs a, pniels* scratch) {
+// Persistent curve kernels of the three verifications (SCHEME 0 single-key, 1 double-key, 2 variable-generator): window tables
+// in a thread-major global scratch region (EC_P_ENTRIES x 128 B per resident thread), the coming window's entries staged into
+// dynamic shared memory by cp.async (16 or 24 uint4 per thread), work handed out per warp from a counter that the preceding
+// challenge kernel reset.
+constexpr int EC_P_ENTRIES = 27;  // three 9-entry tables (the single- and double-key forms use 18)
+constexpr int ec_p_ctas(int scheme) { return scheme == 0 ? 4 : 3; }
+constexpr size_t ec_p_smem(int scheme) { return (size_t)(scheme == 2 ? 24 : 16) * TPB * sizeof(uint4); }
+template <int SCHEME>
+__global__ void __launch_bounds__(TPB, ec_p_ctas(SCHEME)) k_curve_p(const KArgs a, pniels* scratch) {
   const bool aff = (a.flags & SB200_POINTS_AFFINE) != 0;
-  pniels* store = scratch + ((size_t)blockIdx.x * TPB + threadIdx.x) * 18;
+  pniels* store = scratch + ((size_t)blockIdx.x * TPB + threadIdx.x) * EC_P_ENTRIES;
+  extern __shared__ __align__(16) uint4 stage_buf[];
 #if SB_TABLE_STAGE
-  __shared__ uint4 stage_buf[16 * TPB];  // 32 KB: the two entries of the coming window, 8 x 16 bytes each per thread
   uint4* stage = stage_buf;
 #else
   uint4* stage = nullptr;
@@ -600,16 +613,31 @@ __global__ void __launch_bounds__(TPB, EC_P_CTAS) k_verify_ec_p(const KArgs a, p
     const bool active = i < a.n;
     if (!active) i = a.n - 1;
     uint32_t u[8], c[8];
-    ldg_scalar(a.in[1] + i * 8, u);
+    ldg_scalar(a.in[SCHEME == 0 ? 1 : 2] + i * 8, u);
     ldg_scalar(a.out[0] + i * 8, c);
-    bool ok = verify_ec<true>(ldg_point(a.in[0], i, aff), u, ldg_point(a.in[2], i, aff), c, a.combG, store, stage);
+    bool ok;
+    if (SCHEME == 0) {  // in: pk, u, R
+      ok = verify_ec<true>(ldg_point(a.in[0], i, aff), u, ldg_point(a.in[2], i, aff), c, a.combG, store, stage);
+    } else if (SCHEME == 1) {  // in: pk, pk', u, R, R'
+      ok = verify_double_ec<true>(ldg_point(a.in[0], i, aff), ldg_point(a.in[1], i, aff), u, ldg_point(a.in[3], i, aff),
+                                  ldg_point(a.in[4], i, aff), c, a.combG, a.combGp, store, stage);
+    } else {  // in: pk, gen, u, R
+      ok = verify_vargen_ec_auto<true>(ldg_point(a.in[0], i, aff), ldg_point(a.in[1], i, aff), u, ldg_point(a.in[3], i, aff), c, store,
+                                       stage);
+    }
     if (a.flags & SB200_CHECK_POINTS) {  // warp-uniform
+      constexpr int NPT = SCHEME == 0 ? 3 : SCHEME == 1 ? 5 : 4, SKIP = SCHEME == 0 ? 1 : 2;
 #pragma unroll 1
-      for (int k = 0; k < 3; k += 2) ok &= point_well_formed(ldg_point(a.in[k], i, aff));
+      for (int k = 0; k < NPT; k++)
+        if (k != SKIP) ok &= point_well_formed(ldg_point(a.in[k], i, aff));
     }
     unsigned word = __ballot_sync(0xffffffffu, ok && active);
     if ((threadIdx.x & 31) == 0 && active) a.bitmap[i >> 5] = a.inv_mask ? word & ~a.inv_mask[i >> 5] : word;
   }
+}
+template <int SCHEME>
+inline void launch_curve_p(const KArgs& a, unsigned grid, cudaStream_t st) {
+  k_curve_p<SCHEME><<<std::min<unsigned>(grid, (unsigned)(ec_p_ctas(SCHEME) * a.nsm)), TPB, ec_p_smem(SCHEME), st>>>(a, a.ec_scratch);
 }
 
 #endif  // SB_EC_GLOBAL_TABLES
@@ -824,7 +852,7 @@ struct DevCtx {
   Stage hin[2], hout[2];
   std::vector<PendingCopy> pending[2];
   WsState* ws[3] = {nullptr, nullptr, nullptr};  // per pipeline stream, [2] = caller's stream (SB200_DEVICE_PTRS)
-  pniels* ec_scratch[3] = {nullptr, nullptr, nullptr};  // k_verify_ec_p window tables (SB_EC_GLOBAL_TABLES builds only)
+  pniels* ec_scratch[3] = {nullptr, nullptr, nullptr};  // k_curve_p window tables (SB_EC_GLOBAL_TABLES)
   uint32_t* cscratch = nullptr;                  // device-only rows of a SB200_DEVICE_PTRS call (scratch_bytes)
   size_t cscratch_cap = 0;
   cudaEvent_t user_ev = nullptr;                 // last SB200_DEVICE_PTRS work of this context (orders a stream switch)
@@ -930,13 +958,25 @@ int launch(sb200_ctx* ctx, Op op, const KArgs& a, cudaStream_t st) {
     k_run<OP_DECODE_VERIFY><<<grid, TPB, 0, st>>>(dk);
     if (scheme == 0) {
       k_run<OP_CHALLENGE><<<grid, TPB, 0, st>>>(v);
+#if SB_EC_GLOBAL_TABLES
+      launch_curve_p<0>(v, grid, st);
+#else
       k_run<OP_VERIFY_EC><<<grid, TPB, 0, st>>>(v);
+#endif
     } else if (scheme == 1) {
       k_run<OP_CHALLENGE_DOUBLE><<<grid, TPB, 0, st>>>(v);
+#if SB_EC_GLOBAL_TABLES
+      launch_curve_p<1>(v, grid, st);
+#else
       k_run<OP_VERIFY_DOUBLE_EC><<<grid, TPB, 0, st>>>(v);
+#endif
     } else {
       k_run<OP_CHALLENGE_VARGEN><<<grid, TPB, 0, st>>>(v);
+#if SB_EC_GLOBAL_TABLES
+      launch_curve_p<2>(v, grid, st);
+#else
       k_run<OP_VERIFY_VARGEN_EC><<<grid, TPB, 0, st>>>(v);
+#endif
     }
     ctx->launches.fetch_add(3, std::memory_order_relaxed);
     CU(cudaGetLastError());
@@ -946,7 +986,7 @@ int launch(sb200_ctx* ctx, Op op, const KArgs& a, cudaStream_t st) {
   if (op == OP_VERIFY) {  // a.out[0] is always set here: the caller's c_out or scratch
     k_run<OP_CHALLENGE><<<grid, TPB, 0, st>>>(a);
 #if SB_EC_GLOBAL_TABLES
-    k_verify_ec_p<<<std::min<unsigned>(grid, (unsigned)(EC_P_CTAS * a.nsm)), TPB, 0, st>>>(a, a.ec_scratch);
+    launch_curve_p<0>(a, grid, st);
 #else
     k_run<OP_VERIFY_EC><<<grid, TPB, 0, st>>>(a);
 #endif
@@ -957,7 +997,11 @@ int launch(sb200_ctx* ctx, Op op, const KArgs& a, cudaStream_t st) {
 #if SB_VARGEN_SPLIT
   if (op == OP_VERIFY_VARGEN) {
     k_run<OP_CHALLENGE_VARGEN><<<grid, TPB, 0, st>>>(a);
+#if SB_EC_GLOBAL_TABLES
+    launch_curve_p<2>(a, grid, st);
+#else
     k_run<OP_VERIFY_VARGEN_EC><<<grid, TPB, 0, st>>>(a);
+#endif
     ctx->launches.fetch_add(2, std::memory_order_relaxed);
     CU(cudaGetLastError());
     return SB200_OK;
@@ -965,7 +1009,11 @@ int launch(sb200_ctx* ctx, Op op, const KArgs& a, cudaStream_t st) {
 #endif
   if (op == OP_VERIFY_DOUBLE) {
     k_run<OP_CHALLENGE_DOUBLE><<<grid, TPB, 0, st>>>(a);
+#if SB_EC_GLOBAL_TABLES
+    launch_curve_p<1>(a, grid, st);
+#else
     k_run<OP_VERIFY_DOUBLE_EC><<<grid, TPB, 0, st>>>(a);
+#endif
     ctx->launches.fetch_add(2, std::memory_order_relaxed);
     CU(cudaGetLastError());
     return SB200_OK;
@@ -1389,8 +1437,9 @@ int sb200_init_ex(const sb200_params* params_in, const int* devices, int n_devic
         return fail(SB200_ERR_NOMEM);
 #endif
 #if SB_EC_GLOBAL_TABLES
-    for (int s = 0; s < 3; s++)  // 4 x 148 x 128 threads x 2 304 B = 175 MB per stream
-      if (cudaMalloc(&dc.ec_scratch[s], (size_t)EC_P_CTAS * dc.nsm * TPB * 18 * sizeof(pniels)) != cudaSuccess) return fail(SB200_ERR_NOMEM);
+    for (int s = 0; s < 3; s++)  // 4 x 148 x 128 threads x 27 entries x 128 B = 262 MB per stream
+      if (cudaMalloc(&dc.ec_scratch[s], (size_t)4 * dc.nsm * TPB * EC_P_ENTRIES * sizeof(pniels)) != cudaSuccess) return fail(SB200_ERR_NOMEM);
+    if (cudaFuncSetAttribute(k_curve_p<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ec_p_smem(2)) != cudaSuccess) return fail(SB200_ERR_CUDA);
 #endif
     int grid = (COMB_WINDOWS * COMB_ENTRIES + TPB - 1) / TPB;
     k_comb_build<<<grid, TPB, 0, dc.stream[0]>>>(dc.combG, gu, gv);
