@@ -13,7 +13,7 @@ for id in 1 2; do
   if [ -s /tmp/src_${op}_$id.csv ]; then
     head -1 /tmp/src_${op}_$id.csv >> gpurun_out/ncu_${op}_${tag}_opmix.txt
     python tools/ncu_opmix.py /tmp/src_${op}_$id.csv >> gpurun_out/ncu_${op}_${tag}_opmix.txt 2>&1
-    kn=$(head -1 /tmp/src_${op}_$id.csv | sed -E 's/.*(k_run|k_fixed_batch)<\(int\)([0-9]+).*/\1ILi\2E/')
+    kn=$(head -1 /tmp/src_${op}_$id.csv | sed -E 's/.*(k_run|k_fixed_batch|k_curve_p)<\(int\)([0-9]+).*/\1ILi\2E/')
     echo "## kernel $id ($kn): executed warp instructions and stall samples per device function" >> gpurun_out/ncu_${op}_${tag}_byfunc.txt
     python tools/ncu_by_func.py /tmp/src_${op}_$id.csv ${SB200_LIB:-schnorr_b200/libschnorr_b200.so} "$kn" >> gpurun_out/ncu_${op}_${tag}_byfunc.txt 2>&1
   fi
