@@ -116,6 +116,9 @@ int sb200_default_params(int ark_rule, sb200_params* out);
 /* devices: CUDA ordinals to shard over (tuples are split into contiguous blocks, multiples of 32);
  * n_devices = 0 means "device 0".  Validates the parameters, derives and uploads the Hades tables and builds the comb
  * tables of both generators on every device. */
+/* Environment variable read at context creation: SB200_CURVE_PERSISTENT = "always" | "never" selects the form of the curve
+ * kernels of the three verifications regardless of batch size (default: the persistent global-table kernel for batches above one
+ * wave of resident CTAs, the local-memory kernel below; results are identical -- tests run both). */
 int sb200_init_ex(const sb200_params* params, const int* devices, int n_devices, sb200_ctx** out);
 /* = sb200_init_ex(sb200_default_params(SB200_ARK_ENV), ...) */
 int sb200_init(const int* devices, int n_devices, sb200_ctx** out);

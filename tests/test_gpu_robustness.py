@@ -306,3 +306,72 @@ def test_lattice3_on_the_device(engine):
         assert (a - b * c) % N == 0 and (d - b * u) % N == 0, (k, hex(c), hex(u), hex(a), hex(b), hex(d))
         assert max(abs(a), abs(b), abs(d)) < (1 << 174)
     assert n_ok >= 998
+
+
+@pytest.mark.parametrize("mode", ["always", "never"])
+def test_curve_kernel_forms_agree(mode, monkeypatch):
+    """the two forms of the curve kernels -- persistent with global thread-major window tables staged through shared memory
+    (what large batches run) and one-shot with local-memory tables (small batches) -- forced by SB200_CURVE_PERSISTENT on a
+    second context: single-key, double-key and variable-generator verdicts against the oracle on a ragged batch with
+    corrupted, torsion-shifted and small-order inputs, affine and projective"""
+    from schnorr_b200 import Engine
+    monkeypatch.setenv("SB200_CURVE_PERSISTENT", mode)
+    eng = Engine([0])
+    try:
+        rnd = random.Random(46)
+        n = 333
+        tors = V.torsion_points()
+        sk = [rnd.randrange(1, R) for _ in range(n)]
+        nonce = [rnd.randrange(R) for _ in range(n)]
+        msg = [rnd.randrange(Q) for _ in range(n)]
+        # single-key
+        pk = [V.mul(o.G, s) for s in sk]
+        sig = [o.sign(s, k, m, mul=V.mul) for s, k, m in zip(sk, nonce, msg)]
+        u, Rr = [x[0] for x in sig], [x[1] for x in sig]
+        for i in range(n):
+            if i % 3 == 1:
+                u[i] = (u[i] + 1) % R
+            if i % 5 == 2:
+                pk[i] = o.pt_add(pk[i], tors[i % len(tors)])
+            if i % 7 == 3:
+                Rr[i] = o.pt_add(Rr[i], tors[(i + 2) % len(tors)])
+        want = [o.verify(pk[i], u[i], Rr[i], msg[i], mul=V.mul) for i in range(n)]
+        ok, _ = eng.verify(V.points(pk), V.scalars(u), V.points(Rr), V.fqs(msg))
+        assert ok.tolist() == want and any(want) and not all(want)
+        zs = [rnd.randrange(1, Q) for _ in range(n)]
+        ok, _ = eng.verify(V.points(pk, zs), V.scalars(u), V.points(Rr, zs[::-1]), V.fqs(msg), affine=False)
+        assert ok.tolist() == want
+        # double-key
+        m2 = 97
+        pkd = [(V.mul(o.G, s), V.mul(o.G_NUMS, s)) for s in sk[:m2]]
+        sd = [o.sign_double(s, k, m, mul=V.mul) for s, k, m in zip(sk[:m2], nonce[:m2], msg[:m2])]
+        ud, R1, R2 = [x[0] for x in sd], [x[1] for x in sd], [x[2] for x in sd]
+        for i in range(m2):
+            if i % 4 == 1:
+                R2[i] = o.pt_add(R2[i], o.G)
+            if i % 6 == 2:
+                ud[i] = (ud[i] + 5) % R
+        wantd = [o.verify_double(pkd[i][0], pkd[i][1], ud[i], R1[i], R2[i], msg[i], mul=V.mul) for i in range(m2)]
+        ok, _ = eng.verify_double(V.points([p[0] for p in pkd]), V.points([p[1] for p in pkd]), V.scalars(ud), V.points(R1), V.points(R2), V.fqs(msg[:m2]))
+        assert ok.tolist() == wantd and any(wantd) and not all(wantd)
+        # variable generator (with forced full-size fallback lanes: u = r - 1)
+        gens = [V.mul(o.G, rnd.randrange(1, R)) for _ in range(m2)]
+        pkv, uv, Rv = [], [], []
+        for i in range(m2):
+            g = gens[i]
+            if i % 4 == 0:
+                ui, k = R - 1, rnd.randrange(1, R)
+                Rp = V.mul(g, k)
+                c = o.challenge_hash(Rp, msg[i])
+                P = V.mul(g, (k - ui) * pow(c, -1, R) % R)
+            else:
+                ui, Rp, c = o.sign_vargen(sk[i], g, nonce[i], msg[i], mul=V.mul)
+                P = V.mul(g, sk[i])
+            if i % 3 == 1:
+                Rp = o.pt_add(Rp, g)
+            pkv.append(P); uv.append(ui); Rv.append(Rp)
+        wantv = [o.verify_vargen(pkv[i], gens[i], uv[i], Rv[i], msg[i], mul=V.mul) for i in range(m2)]
+        ok, _ = eng.verify_vargen(V.points(pkv), V.points(gens), V.scalars(uv), V.points(Rv), V.fqs(msg[:m2]))
+        assert ok.tolist() == wantv and any(wantv) and not all(wantv)
+    finally:
+        eng.close()
