@@ -587,8 +587,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_verify_ws(const KArgs a) {
 // in a thread-major global scratch region (EC_P_ENTRIES x 128 B per resident thread), the coming window's entries staged into
 // dynamic shared memory by cp.async (16 or 24 uint4 per thread), work handed out per warp from a counter that the preceding
 // challenge kernel reset.
+#ifndef SB_EC_P_CTAS_ALL4
+#define SB_EC_P_CTAS_ALL4 1  // 4 CTAs per SM (128 registers) for the double-key and variable-generator forms too: with the tables out of
+                             // local memory the spills are cheap -- measured 12.07 -> 12.50 and 18.05 -> 18.45 M verifies/s against 3 CTAs at 168
+#endif
 constexpr int EC_P_ENTRIES = 27;  // three 9-entry tables (the single- and double-key forms use 18)
-constexpr int ec_p_ctas(int scheme) { return scheme == 0 ? 4 : 3; }
+constexpr int ec_p_ctas(int scheme) { return SB_EC_P_CTAS_ALL4 ? 4 : (scheme == 0 ? 4 : 3); }
 constexpr size_t ec_p_smem(int scheme) { return (size_t)(scheme == 2 ? 24 : 16) * TPB * sizeof(uint4); }
 template <int SCHEME>
 __global__ void __launch_bounds__(TPB, ec_p_ctas(SCHEME)) k_curve_p(const KArgs a, pniels* scratch) {
