@@ -11,6 +11,6 @@ for lib in "" $v "" $v; do
 done
 echo "=== pytest lib${v} (single-key verify tests)" >> $out
 SB200_LIB=$PWD/schnorr_b200/libschnorr_b200${v}.so timeout 900 python -m pytest tests -m gpu -q -k "verify_single or small_order or config1 or golden or half_size or sign_and_verify" >> $out 2>&1
-SB200_LIB=$PWD/schnorr_b200/libschnorr_b200${v}.so ncu --set full --clock-control none --kernel-name-base demangled -k regex:k_verify_ec_p --launch-skip 1 -c 1 -f -o /tmp/gt python tools/prof_op.py verify 20 1 > gpurun_out/ab_gt_ncu.log 2>&1
+SB200_LIB=$PWD/schnorr_b200/libschnorr_b200${v}.so ncu --set full --clock-control none --kernel-name-base demangled -k regex:k_curve_p --launch-skip 1 -c 1 -f -o /tmp/gt python tools/prof_op.py verify 20 1 > gpurun_out/ab_gt_ncu.log 2>&1
 python tools/ncu_summary.py /tmp/gt.ncu-rep | grep -v fp64 > gpurun_out/ab_gt_ncu_summary.txt 2>&1
 grep -E "===|verify n|passed|failed" $out; grep -E "gpu__time|dram|issue_active|long_scoreboard|short_scoreboard|lg_throttle|warps_active" gpurun_out/ab_gt_ncu_summary.txt
