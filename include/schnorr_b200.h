@@ -78,7 +78,8 @@ enum {
  * no branch depends on the nonce or the secret key (the reference's ladder is a constant-time select).  Fixed base:
  * 4-bit combs of G and G' staged in shared memory and read by masked scan (64 additions instead of the 16 of the
  * default 16-bit comb, whose 50 MB table in HBM is indexed with scalar digits); variable base: the window table is
- * scanned instead of indexed.  Same outputs bit for bit; slower (DESIGN.md 4.2 has the measured ratio). */
+ * scanned instead of indexed; the conversion to affine form keeps Fermat's fixed-length a^(q-2) instead of the Euclidean
+ * inversion (whose running time depends on its input).  Same outputs bit for bit; slower (DESIGN.md 4.2 has the measured ratio). */
 #define SB200_SIGN_OBLIVIOUS 16u
 
 /* ---- scheme parameters ------------------------------------------------------------------------------------------
