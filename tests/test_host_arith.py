@@ -466,3 +466,31 @@ def test_euclidean_inversion_equals_fermat(lib):
         want = pow(a, Q - 2, Q)
         assert H.unmont(out) == want, hex(a)
         assert (out == ref).all()
+
+
+def test_hgcd_double_precision_quotient_never_overshoots():
+    """csrc/hgcd.cuh estimates the Euclid's partial quotient as floor(double(R0) / (double(R1) + 1) * (1 - 2^-50)) from the top 64
+    bits of the two remainders.  The step is only valid if that never exceeds floor(R0 / (R1 + 1)) (<= floor(r0 / r1)): checked
+    here in IEEE double arithmetic (Python floats) on random and adversarial 64-bit pairs -- exact multiples, neighbours of
+    powers of two, values whose conversion to double rounds up."""
+    rnd = random.Random(99)
+    k = 0.99999999999999911182158029987
+    assert k == 1.0 - 2.0 ** -50
+    pairs = []
+    for _ in range(20000):
+        r1 = rnd.getrandbits(rnd.randrange(1, 65))
+        q = rnd.getrandbits(rnd.randrange(1, 33))
+        pairs.append((min(q * (r1 + 1) + rnd.choice([0, 0, 1, r1]), (1 << 64) - 1), r1))   # at or just above an exact multiple
+        pairs.append((rnd.getrandbits(64), rnd.getrandbits(rnd.randrange(1, 65))))
+    for e in range(1, 64):
+        for d in (-1, 0, 1):
+            pairs += [((1 << 64) - 1, (1 << e) + d), ((1 << 63) + d + 1, (1 << e) + d), ((1 << 53) + (1 << e) + d, (1 << (e % 53)) + 1)]
+    pairs += [((1 << 64) - 1, 0), ((1 << 64) - 1, (1 << 64) - 1), ((1 << 64) - 1, (1 << 64) - 2), (1, 0), (0, 5)]
+    for R0, R1 in pairs:
+        if R1 < 0:
+            continue
+        est = int(float(R0) / (float(R1) + 1.0) * k)
+        true = R0 // (R1 + 1)
+        assert est <= true, (R0, R1, est, true)
+        # an underestimate only costs an extra step; below the clamp (2^31 - 1) it is at most one
+        assert est >= min(true, (1 << 31) - 1) - 1, (R0, R1, est, true)
