@@ -587,12 +587,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_verify_ws(const KArgs a) {
 // in a thread-major global scratch region (EC_P_ENTRIES x 128 B per resident thread), the coming window's entries staged into
 // dynamic shared memory by cp.async (16 or 24 uint4 per thread), work handed out per warp from a counter that the preceding
 // challenge kernel reset.
+#ifndef SB_EC_P_CTAS0
+#define SB_EC_P_CTAS0 4  // resident CTAs per SM of the single-key curve kernel; measured 4 / 5 / 6 (128 / 96 / 80 registers): 24.93 / 24.95 / 25.02 M verifies/s -- occupancy is not the limiter
+#endif
 #ifndef SB_EC_P_CTAS_ALL4
 #define SB_EC_P_CTAS_ALL4 1  // 4 CTAs per SM (128 registers) for the double-key and variable-generator forms too: with the tables out of
                              // local memory the spills are cheap -- measured 12.07 -> 12.50 and 18.05 -> 18.45 M verifies/s against 3 CTAs at 168
 #endif
 constexpr int EC_P_ENTRIES = 27;  // three 9-entry tables (the single- and double-key forms use 18)
-constexpr int ec_p_ctas(int scheme) { return SB_EC_P_CTAS_ALL4 ? 4 : (scheme == 0 ? 4 : 3); }
+constexpr int ec_p_ctas(int scheme) { return (SB_EC_P_CTAS0 != 4 && scheme == 0) ? SB_EC_P_CTAS0 : (SB_EC_P_CTAS_ALL4 ? 4 : (scheme == 0 ? 4 : 3)); }
 constexpr size_t ec_p_smem(int scheme) { return (size_t)(scheme == 2 ? 24 : 16) * TPB * sizeof(uint4); }
 template <int SCHEME>
 __global__ void __launch_bounds__(TPB, ec_p_ctas(SCHEME)) k_curve_p(const KArgs a, pniels* scratch) {
@@ -1453,7 +1456,7 @@ int sb200_init_ex(const sb200_params* params_in, const int* devices, int n_devic
 #endif
 #if SB_EC_GLOBAL_TABLES
     for (int s = 0; s < 3; s++)  // 4 x 148 x 128 threads x 27 entries x 128 B = 262 MB per stream
-      if (cudaMalloc(&dc.ec_scratch[s], (size_t)4 * dc.nsm * TPB * EC_P_ENTRIES * sizeof(pniels)) != cudaSuccess) return fail(SB200_ERR_NOMEM);
+      if (cudaMalloc(&dc.ec_scratch[s], (size_t)(SB_EC_P_CTAS0 > 4 ? SB_EC_P_CTAS0 : 4) * dc.nsm * TPB * EC_P_ENTRIES * sizeof(pniels)) != cudaSuccess) return fail(SB200_ERR_NOMEM);
     if (cudaFuncSetAttribute(k_curve_p<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ec_p_smem(2)) != cudaSuccess) return fail(SB200_ERR_CUDA);
 #endif
     int grid = (COMB_WINDOWS * COMB_ENTRIES + TPB - 1) / TPB;
